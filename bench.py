@@ -1,0 +1,290 @@
+# coding: utf-8
+"""Benchmark of the autoregressive synthesis path (BASELINE.json metric: audio samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--utts-per-gpu U]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: one ``incremental_forward`` of BASELINE
+config 2 (MoL 10-mixture, 24 layers / 4 stacks, 512 residual / 512 gate / 256 skip channels,
+80-dim mel conditioning, 22.05 kHz, T = 22050 samples) for ``U`` utterance(s) per GPU (default 1;
+U=8 is BASELINE config 4's per-GPU share).  Utterances are independent, so N GPUs run N x U
+utterances with no data-path collective ("weak" scaling); NCCL carries only the barrier, the
+max-over-ranks time and the final waveform gather.
+
+  value   : samples/s, whole job, conditioning already resident in HBM (kernel launches only)
+  e2e     : the same through WaveNet.incremental_forward() from pinned HOST mel frames to a HOST
+            waveform (H2D of the mel, upsample network, kernel, D2H of the result inside the timed
+            region)
+  roofline: weight-streaming bound.  One launch generates T samples and every sample needs all
+            fp32 weights of the stack once (98.72 MB/step for config 2), so
+            algorithmic bytes/launch = T x weight_bytes_per_step; peak = measured HBM copy
+            bandwidth from MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the oracle port of the reference's CPU incremental_forward
+            (same ATen op sequence per sample; the reference itself is Python and is not present on
+            the GPU box) timed on the host cores over a bounded number of samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG2 = dict(out_channels=30, layers=24, stacks=4, residual_channels=512, gate_channels=512,
+            skip_out_channels=256, cin_channels=80, cin_pad=2, gin_channels=-1, scalar_input=True,
+            output_distribution="Logistic", dropout=0.0, upsample_conditional_features=True,
+            upsample_params={"upsample_scales": [4, 4, 4, 4], "cin_channels": 80, "cin_pad": 2})
+SAMPLE_RATE = 22050
+T_FULL = 22050
+HOP = 256
+
+
+def build_model(seed=0):
+    from wavenet_vocoder_b200 import WaveNet
+    torch.manual_seed(seed)
+    m = WaveNet(**CFG2).eval()
+    with torch.no_grad():
+        m.last_conv_layers[3].bias[20:] -= 3.0      # log-scales ~ -3: non-degenerate waveform
+    return m
+
+
+def oracle_parts(model):
+    from oracle import wavenet_oracle as orc
+    cfg = orc.PathConfig(out_channels=30, layers=24, stacks=4, residual_channels=512, gate_channels=512,
+                         skip_out_channels=256, kernel_size=3, cin_channels=80, gin_channels=-1,
+                         scalar_input=True, output_distribution="Logistic")
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    return orc, cfg, orc.weights_from_state_dict(cfg, sd)
+
+
+def time_cpu_port(model, n_samples, warm, threads):
+    """The reference algorithm on the host: samples/s over ``n_samples`` steps after ``warm``."""
+    orc, cfg, w = oracle_parts(model)
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1)
+    T = warm + n_samples
+    c = torch.randn(1, 80, T, generator=gen)
+    marks = {}
+
+    def progress(it):
+        for t in it:
+            if t == warm:
+                marks["t0"] = time.perf_counter()
+            yield t
+    torch.manual_seed(0)
+    with torch.no_grad():
+        orc.incremental_forward(cfg, w, c=c, T=T, progress=progress)
+    dt = time.perf_counter() - marks["t0"]
+    return n_samples / dt, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: CPU port of the reference path, rank 0 only."""
+    if rank != 0:
+        return
+    model = build_model()
+    threads = os.cpu_count() or 1
+    n = args.ref_samples
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = time_cpu_port(model, n, 20, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    sps = sum(n for _ in vals) / sum(dt for _, dt in vals)
+    line = {
+        "impl": "reference", "metric": "audio samples/sec (22.05 kHz MoL, 24-layer)", "value": sps,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf": SAMPLE_RATE / sps,
+        "config": {"workload": "BASELINE config 2: MoL-10 24L/4 stacks 512/512/256, 80-mel, B=1; "
+                               "each step = %d samples of the same per-sample loop on the host CPU" % n},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": "%d samples after 20 warm-up samples per step, torch CPU fp32, %d threads" % (n, threads)},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utts-per-gpu", type=int, default=1)
+    ap.add_argument("--T", type=int, default=T_FULL)
+    ap.add_argument("--ref-samples", type=int, default=1500)
+    ap.add_argument("--cpu-samples", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, U, T = max(args.warmup, 3), args.steps, args.utts_per_gpu, args.T
+
+    model = build_model().to(dev)
+    eng = model._get_engine()
+    plan = eng.plan(U)
+    # synthetic mel ~ N(0,1) (mean-var normalised features, compute-meanvar-stats.py:25-32)
+    frames = -(-T // HOP) + 2 * CFG2["cin_pad"]
+    T_up = (frames - 2 * CFG2["cin_pad"]) * HOP
+    gen = torch.Generator().manual_seed(1000 + rank)
+    mel_host = torch.randn(U, 80, frames, generator=gen).pin_memory()
+    with torch.no_grad():
+        c_dev = model.upsample_net(mel_host.to(dev))[:, :, :T].transpose(1, 2).contiguous()   # (U,T,80) resident
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)       # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step(i):
+        out, _ = eng.generate(B=U, T=T, c=c_dev, seed=i, sync=False)
+        return out
+
+    def e2e_step(i):
+        y = model.incremental_forward(c=mel_host, T=T_up, seed=i)
+        return y.cpu()
+
+    results = {}
+    for name, fn, Tn in (("device", device_step, T), ("e2e", e2e_step, T_up)):
+        for i in range(W):
+            fn(i)
+            eng.sync()
+        launches0 = eng.plan(U)["launches"]
+        clk = ClockSampler(local)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        if rank == 0:
+            clk.start()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                                           # flush L2 between timed iterations
+            ev[i][0].record()
+            out = fn(W + i)
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = clk.stop() if rank == 0 else None
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if name == "e2e":
+            ms = t_wall * 1e3          # host-side copies are part of the e2e path: wall clock, flushes included
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        results[name] = dict(ms=float(t.item()), samples=Tn * U * world * K, clocks=clocks,
+                             launches=eng.plan(U)["launches"] - launches0)
+    if dist is not None:
+        # the only data-path collective: gather the waveforms of the last step on rank 0
+        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out, gathered, dst=0)
+        torch.cuda.synchronize(dev)
+
+    if rank == 0:
+        d, e = results["device"], results["e2e"]
+        sps = d["samples"] / (d["ms"] * 1e-3)
+        e_sps = e["samples"] / (e["ms"] * 1e-3)
+        peak, peak_src = measured_peak()
+        steps_per_s_per_gpu = (T * K) / (d["ms"] * 1e-3)             # generated time steps per second on one GPU
+        achieved = steps_per_s_per_gpu * plan["weight_bytes_per_step"] / 1e9
+        line = {
+            "metric": "audio samples/sec (22.05 kHz MoL, 24-layer)", "value": sps, "unit": "samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": d["ms"] / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "rtf": SAMPLE_RATE * U * world / sps, "x_realtime_per_utterance": sps / (U * world) / SAMPLE_RATE,
+            "config": {"workload": "BASELINE config 2: MoL-10, 24 layers / 4 stacks, 512/512/256 ch, 80-mel local "
+                                   "conditioning, T=%d, %d utterance(s) per GPU" % (T, U),
+                       "global_batch": U * world, "T": T, "parallelism": "utterance-sharded x%d" % world,
+                       "l2": "256 MiB write between timed iterations; weights (98.7 MB) re-read every sample",
+                       "plan": {k: plan[k] for k in ("num_ctas", "batch_tile", "resident_blobs", "ring_slots",
+                                                     "exchange_copies", "exchanges_per_step", "smem_bytes",
+                                                     "rings_in_smem", "streamed_bytes_per_step")}},
+            "clocks": d["clocks"],
+            "e2e": {"value": e_sps, "unit": "samples/s",
+                    "h2d_bytes_per_step": int(mel_host.numel() * 4), "d2h_bytes_per_step": int(U * T_up * 4),
+                    "T": T_up, "api": "WaveNet.incremental_forward(c=host mel) -> .cpu()", "clocks": e["clocks"]},
+            "gpu_launches": d["launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": T * plan["weight_bytes_per_step"],
+                         "flops_per_sample": plan["flops_per_sample"],
+                         "fp32_tflops_achieved": sps * plan["flops_per_sample"] / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt = time_cpu_port(model.cpu(), args.cpu_samples, 100, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": "%d samples after 100 warm-up samples of the same config-2 loop "
+                                              "(oracle port of the reference CPU incremental_forward, torch fp32, "
+                                              "%d threads, %.1f s)" % (args.cpu_samples, threads, dt)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

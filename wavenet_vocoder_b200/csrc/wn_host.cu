@@ -1,0 +1,759 @@
+// wn_host.cu — libwn.so: planner, weight packer and the C ABI declared in include/wn.h.
+// Built for sm_100a only:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/wn.h"
+#include "wn_plan.h"
+#include "wn_kernel.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            return fail(WN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+        }                                                                                       \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------
+// planner (pure host arithmetic; exercised without a GPU through wn_plan_only / wn_pack_cta)
+// ------------------------------------------------------------------------------------------
+static int align_up(long long v, int a) { return (int)(((v + a - 1) / a) * a); }
+
+static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long smem_cap, WnPlan& pl,
+                          std::vector<int>& ringtab) {
+    memset(&pl, 0, sizeof(pl));
+    if (c.abi_version != WN_ABI_VERSION) return fail(WN_ERR_INVALID, "wn_config.abi_version mismatch");
+    if (c.layers < 1 || c.stacks < 1 || c.layers % c.stacks != 0)
+        return fail(WN_ERR_INVALID, "layers must be a positive multiple of stacks (wavenet.py:117)");
+    if (c.gate_channels < 2 || (c.gate_channels & 1)) return fail(WN_ERR_INVALID, "gate_channels must be even");
+    if (c.kernel_size < 1 || c.kernel_size > 8) return fail(WN_ERR_INVALID, "kernel_size out of range [1,8]");
+    if (c.residual_channels < 1 || c.skip_channels < 1 || c.out_channels < 1)
+        return fail(WN_ERR_INVALID, "channel counts must be positive");
+    const int maxK = WN_MAXE * WN_NT;
+    if (c.residual_channels > maxK || c.gate_channels / 2 > maxK || c.skip_channels > maxK || c.out_channels > maxK)
+        return fail(WN_ERR_INVALID, "a stage vector exceeds 1024 entries (unsupported shape)");
+    if (c.cin_channels < 0 || c.cin_channels > 32 * WN_MAX_CI)
+        return fail(WN_ERR_INVALID, "cin_channels must be in [0,128]");
+    if (c.gin_channels < 0) return fail(WN_ERR_INVALID, "gin_channels must be >= 0");
+    if (c.layers / c.stacks > 20) return fail(WN_ERR_INVALID, "dilation 2^(layers/stacks) too large");
+    if (c.input_kind == WN_INPUT_SCALAR) {
+        if (c.head_kind == WN_HEAD_MOL) {
+            if (c.out_channels % 3 != 0) return fail(WN_ERR_INVALID, "MoL head needs out_channels % 3 == 0 (mixture.py:130)");
+        } else if (c.head_kind == WN_HEAD_GAUSS) {
+            if (c.out_channels != 2 && c.out_channels % 3 != 0)
+                return fail(WN_ERR_INVALID, "Gaussian head needs out_channels == 2 or % 3 == 0 (mixture.py:229-234)");
+        } else
+            return fail(WN_ERR_INVALID, "scalar input needs a MoL or Gaussian head (wavenet.py:322-330)");
+    } else if (c.input_kind == WN_INPUT_ONEHOT) {
+        if (c.head_kind != WN_HEAD_SOFTMAX) return fail(WN_ERR_INVALID, "one-hot input needs the softmax head");
+    } else
+        return fail(WN_ERR_INVALID, "bad input_kind");
+    if (batch < 1) return fail(WN_ERR_INVALID, "batch must be >= 1");
+    if (num_sms < 1) return fail(WN_ERR_INVALID, "no SMs");
+
+    pl.L = c.layers;
+    pl.per_stack = c.layers / c.stacks;
+    pl.R = c.residual_channels;
+    pl.G = c.gate_channels;
+    pl.G2 = c.gate_channels / 2;
+    pl.S = c.skip_channels;
+    pl.O = c.out_channels;
+    pl.kw = c.kernel_size;
+    pl.C = c.cin_channels;
+    pl.gin = c.gin_channels;
+    pl.input_kind = c.input_kind;
+    pl.head_kind = c.head_kind;
+    pl.Kmix = (c.head_kind == WN_HEAD_SOFTMAX) ? 0 : (c.out_channels == 2 ? 1 : c.out_channels / 3);
+    pl.skip_scale = (float)sqrt(1.0 / (double)c.layers);
+    pl.BT = batch <= 1 ? 1 : (batch <= 2 ? 2 : (batch <= 4 ? 4 : 8));
+    const int BT = pl.BT;
+
+    // ---- how many blocks: every block must own at least one gate pair
+    int P = c.num_ctas > 0 ? c.num_ctas : env_int("WN_NUM_CTAS", 0);
+    if (P <= 0) {
+        const int cap = std::min(num_sms, pl.G2);
+        const int per = wn_ceil_div(pl.G2, cap);
+        P = wn_ceil_div(pl.G2, per);
+    }
+    if (P > num_sms) return fail(WN_ERR_INVALID, "num_ctas exceeds the SM count (blocks must be co-resident)");
+    if (P > pl.G2) return fail(WN_ERR_INVALID, "num_ctas exceeds gate_channels/2");
+    pl.P = P;
+    pl.NYm = wn_ceil_div(pl.G2, P);
+    pl.NXm = wn_ceil_div(pl.R, P);
+    pl.NSm = wn_ceil_div(pl.S, P);
+    pl.NAm = wn_ceil_div(pl.S, P);
+    pl.NBm = wn_ceil_div(pl.O, P);
+    pl.RA = 2 * pl.NYm;
+    pl.NQ_A = wn_ceil_div(pl.RA, 4);
+    pl.RA4 = 4 * pl.NQ_A;
+    pl.NQ_D = wn_ceil_div((pl.kw - 1) * pl.RA, 4);
+    pl.NQ_BO = wn_ceil_div(pl.NXm, 4);
+    pl.NQ_BS = wn_ceil_div(pl.NSm, 4);
+    pl.NQ_HA = wn_ceil_div(pl.NAm, 4);
+    pl.NQ_HB = wn_ceil_div(pl.NBm, 4);
+    const int half = WN_NT / 2;
+    if (pl.NYm * BT > half || pl.NXm * BT > half || pl.NSm * BT > half || pl.NAm * BT > half ||
+        pl.NBm * BT > half || (pl.kw - 1) * pl.RA * BT > half)
+        return fail(WN_ERR_INVALID, "too many rows per block for this batch tile (use more blocks)");
+
+    // ---- blobs
+    int o = 0;
+    pl.lb_Acrit = o; o += pl.NQ_A * pl.R * 4;
+    pl.lb_Adef = o;  o += pl.NQ_D * pl.R * 4;
+    pl.lb_convb = o; o += pl.RA4;
+    pl.lb_Bo = o;    o += pl.NQ_BO * pl.G2 * 4;
+    pl.lb_Bs = o;    o += pl.NQ_BS * pl.G2 * 4;
+    pl.lb_outb = o;  o += 4 * pl.NQ_BO;
+    pl.lb_skipb = o; o += 4 * pl.NQ_BS;
+    pl.lb_floats = align_up(o, 4);
+    o = 0;
+    pl.hb_Ha = o;  o += pl.NQ_HA * pl.S * 4;
+    pl.hb_Hab = o; o += 4 * pl.NQ_HA;
+    pl.hb_Hb = o;  o += pl.NQ_HB * pl.S * 4;
+    pl.hb_Hbb = o; o += 4 * pl.NQ_HB;
+    pl.hb_floats = align_up(o, 4);
+    pl.slot_floats = align_up(std::max(pl.lb_floats, pl.hb_floats), 32);
+    pl.cta_w_floats = (long long)pl.L * pl.lb_floats + pl.hb_floats;
+    pl.nblobs = pl.L + 1;
+    pl.cta_cw_floats = (long long)pl.L * pl.NQ_A * pl.C * 4;
+
+    // ---- exchange map
+    pl.NE = 2 * pl.L + 2;
+    int nc = c.exchange_copies > 0 ? c.exchange_copies : env_int("WN_NCOPY", 0);
+    if (nc <= 0) nc = std::max(1, std::min(8, P / 16));
+    pl.ncopy = std::min(nc, P);
+    pl.ex_x = 0;
+    pl.ex_y = pl.L * pl.R;
+    pl.ex_sk = pl.ex_y + pl.L * pl.G2;
+    pl.ex_h1 = pl.ex_sk + pl.S;
+    pl.ex_h2 = pl.ex_h1 + pl.S;
+    pl.ex_elems = pl.ex_h2 + pl.O;
+    // replicas 4 KiB + 256 B apart so that they do not alias onto the same L2 slices
+    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + 511) / 512) * 512 + 32;
+
+    // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later
+    ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);
+    long long pos = 0;
+    for (int l = 0; l < pl.L; ++l)
+        for (int k = 0; k < pl.kw - 1; ++k) {
+            const int D = (pl.kw - 1 - k) * wn_dilation(pl, l);
+            ringtab[((size_t)l * (pl.kw - 1) + k) * 2] = (int)pos;
+            ringtab[((size_t)l * (pl.kw - 1) + k) * 2 + 1] = D;
+            pos += D;
+        }
+    pl.ring_pos_total = pos;
+    const long long ring_bytes = pos * pl.RA4 * BT * 4;
+
+    // ---- shared memory map
+    auto layout = [&](bool ring_smem) -> long long {
+        long long off = 0;
+        auto take = [&](long long bytes, int al) {
+            off = ((off + al - 1) / al) * al;
+            long long r = off;
+            off += bytes;
+            return (int)r;
+        };
+        pl.sm_bar = take((long long)(2 * pl.nblobs + 8) * 8, 16);
+        pl.sm_misc = take(16, 16);
+        pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
+        pl.sm_ringtab = take((long long)ringtab.size() * 4 + 16, 16);
+        pl.sm_xs = take((long long)pl.R * BT * 4, 16);
+        const int nq1 = std::max(std::max(pl.NQ_A, pl.NQ_BO), std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
+        pl.sm_red1 = take((long long)nq1 * 4 * BT * WN_NWARP * 4, 16);
+        pl.sm_red2 = take((long long)(pl.NQ_D + pl.NQ_BS) * 4 * BT * WN_NWARP * 4 + 16, 16);
+        pl.sm_sb = take((long long)pl.L * pl.RA4 * BT * 4, 16);
+        pl.sm_cond = take(pl.C > 0 ? 2LL * pl.L * pl.RA4 * BT * 4 : 16, 16);
+        pl.sm_skipacc = take((long long)pl.NSm * BT * 4 + 16, 16);
+        pl.sm_hs = take((long long)pl.O * BT * 4, 16);
+        pl.sm_noise = take((long long)BT * (pl.O + 2) * 4, 16);
+        pl.sm_first = take(2LL * pl.R * 4, 16);
+        pl.sm_ring = take(ring_smem ? ring_bytes : 16, 16);
+        pl.sm_slots = take(0, 128);
+        return off;
+    };
+    const long long slot_bytes = (long long)pl.slot_floats * 4;
+    const int want_ring_smem = env_int("WN_RING_SMEM", -1);
+    bool ring_smem = (want_ring_smem != 0) && ring_bytes <= 96 * 1024;
+    long long fixed = layout(ring_smem);
+    long long fit = (smem_cap - fixed) / slot_bytes;
+    if (ring_smem && want_ring_smem < 0 && fit < std::min<long long>(pl.nblobs, 3)) {
+        ring_smem = false;
+        fixed = layout(false);
+        fit = (smem_cap - fixed) / slot_bytes;
+    }
+    pl.ring_in_smem = ring_smem ? 1 : 0;
+    if (fit >= pl.nblobs) {
+        pl.nres = pl.nblobs;
+        pl.nring = 0;
+    } else {
+        if (fit < 2) return fail(WN_ERR_INVALID, "shared memory too small for two weight slots (use more blocks)");
+        int nr = c.ring_slots > 0 ? c.ring_slots : env_int("WN_RING_SLOTS", 3);
+        nr = (int)std::max<long long>(2, std::min<long long>(nr, fit));
+        pl.nring = nr;
+        pl.nres = (int)fit - nr;
+        const int force_res = env_int("WN_RESIDENT", -1);
+        if (force_res >= 0 && force_res < pl.nres) pl.nres = force_res;
+    }
+    pl.smem_bytes = (int)(pl.sm_slots + (long long)(pl.nres + pl.nring) * slot_bytes);
+    if (pl.smem_bytes > smem_cap) return fail(WN_ERR_INVALID, "shared memory map exceeds the per-block limit");
+    return WN_OK;
+}
+
+static void fill_info(const wn_config& c, const WnPlan& pl, wn_plan_info* out) {
+    memset(out, 0, sizeof(*out));
+    out->num_ctas = pl.P;
+    out->threads_per_cta = WN_NTHREADS;
+    out->batch_tile = pl.BT;
+    out->rows_y = pl.NYm;
+    out->rows_x = pl.NXm;
+    out->rows_skip = pl.NSm;
+    out->rows_head_a = pl.NAm;
+    out->rows_head_b = pl.NBm;
+    out->resident_blobs = pl.nres;
+    out->ring_slots = pl.nring;
+    out->blobs_per_step = pl.nblobs;
+    out->exchange_copies = pl.ncopy;
+    out->exchanges_per_step = pl.NE;
+    out->rings_in_smem = pl.ring_in_smem;
+    out->smem_bytes = pl.smem_bytes;
+    out->layer_blob_bytes = (int64_t)pl.lb_floats * 4;
+    out->head_blob_bytes = (int64_t)pl.hb_floats * 4;
+    out->packed_bytes_per_cta = (int64_t)pl.cta_w_floats * 4;
+    out->cond_packed_bytes_per_cta = (int64_t)pl.cta_cw_floats * 4;
+    const int64_t cin0 = (c.input_kind == WN_INPUT_SCALAR) ? 1 : pl.O;
+    // MAC = C0*R + L*(G*kw*R + G*C + S*G/2 + R*G/2) + S*S + O*S ; weights = MAC + biases
+    const int64_t mac = cin0 * pl.R + (int64_t)pl.L * ((int64_t)pl.G * pl.kw * pl.R + (int64_t)pl.G * pl.C +
+                                                        (int64_t)pl.S * pl.G2 + (int64_t)pl.R * pl.G2) +
+                        (int64_t)pl.S * pl.S + (int64_t)pl.O * pl.S;
+    const int64_t biases = pl.R + (int64_t)pl.L * (pl.G + pl.S + pl.R) + pl.S + pl.O;
+    out->flops_per_sample = 2 * mac;
+    out->weight_bytes_per_step = 4 * (mac + biases);
+    int64_t streamed = 0;
+    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += (i < pl.L ? pl.lb_floats : pl.hb_floats) * 4LL;
+    out->streamed_bytes_per_step = streamed * pl.P;
+}
+
+// ------------------------------------------------------------------------------------------
+// packer
+// ------------------------------------------------------------------------------------------
+static inline void put_q(float* grp, int K, int rowidx, int k, float v) {
+    grp[((size_t)(rowidx >> 2) * K + k) * 4 + (rowidx & 3)] = v;
+}
+
+// packed image of block `p`: L layer blobs then the head blob (all zero-padded)
+static void pack_cta(const WnPlan& pl, const wn_weights& w, int p, float* out) {
+    memset(out, 0, (size_t)pl.cta_w_floats * sizeof(float));
+    int y0, ny, x0, nx, s0, ns, a0, na, b0, nb;
+    wn_part(pl.G2, pl.P, p, y0, ny);
+    wn_part(pl.R, pl.P, p, x0, nx);
+    wn_part(pl.S, pl.P, p, s0, ns);
+    wn_part(pl.S, pl.P, p, a0, na);
+    wn_part(pl.O, pl.P, p, b0, nb);
+    const int R = pl.R, G2 = pl.G2, kw = pl.kw, S = pl.S;
+    for (int l = 0; l < pl.L; ++l) {
+        const wn_layer_weights& lw = w.layers[l];
+        float* blob = out + (size_t)l * pl.lb_floats;
+        for (int j = 0; j < ny; ++j)
+            for (int ab = 0; ab < 2; ++ab) {
+                const int rr = 2 * j + ab;                       // a_j, b_j interleaved
+                const int grow = ab ? G2 + y0 + j : y0 + j;      // modules.py:138 split
+                const float* row = lw.conv_w + (size_t)grow * kw * R;   // conv.py:56-61: col = k*R + r
+                for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Acrit, R, rr, k, row[(size_t)(kw - 1) * R + k]);
+                for (int tap = 0; tap < kw - 1; ++tap)
+                    for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Adef, R, tap * pl.RA + rr, k, row[(size_t)tap * R + k]);
+                blob[pl.lb_convb + rr] = lw.conv_b ? lw.conv_b[grow] : 0.f;
+            }
+        for (int r = 0; r < nx; ++r) {
+            const float* row = lw.out_w + (size_t)(x0 + r) * G2;
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Bo, G2, r, k, row[k]);
+            blob[pl.lb_outb + r] = lw.out_b ? lw.out_b[x0 + r] : 0.f;
+        }
+        for (int r = 0; r < ns; ++r) {
+            const float* row = lw.skip_w + (size_t)(s0 + r) * G2;
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Bs, G2, r, k, row[k]);
+            blob[pl.lb_skipb + r] = lw.skip_b ? lw.skip_b[s0 + r] : 0.f;
+        }
+    }
+    float* hb = out + (size_t)pl.L * pl.lb_floats;
+    for (int r = 0; r < na; ++r) {
+        const float* row = w.last_a_w + (size_t)(a0 + r) * S;
+        for (int k = 0; k < S; ++k) put_q(hb + pl.hb_Ha, S, r, k, row[k]);
+        hb[pl.hb_Hab + r] = w.last_a_b ? w.last_a_b[a0 + r] : 0.f;
+    }
+    for (int r = 0; r < nb; ++r) {
+        const float* row = w.last_b_w + (size_t)(b0 + r) * S;
+        for (int k = 0; k < S; ++k) put_q(hb + pl.hb_Hb, S, r, k, row[k]);
+        hb[pl.hb_Hbb + r] = w.last_b_b ? w.last_b_b[b0 + r] : 0.f;
+    }
+}
+
+static void pack_cw_cta(const WnPlan& pl, const wn_weights& w, int p, float* out) {
+    if (pl.C <= 0) return;
+    memset(out, 0, (size_t)pl.cta_cw_floats * sizeof(float));
+    int y0, ny;
+    wn_part(pl.G2, pl.P, p, y0, ny);
+    for (int l = 0; l < pl.L; ++l) {
+        const float* cwm = w.layers[l].cond_w;
+        float* grp = out + (size_t)l * pl.NQ_A * pl.C * 4;
+        for (int j = 0; j < ny; ++j)
+            for (int ab = 0; ab < 2; ++ab) {
+                const int rr = 2 * j + ab, grow = ab ? pl.G2 + y0 + j : y0 + j;
+                for (int ch = 0; ch < pl.C; ++ch) put_q(grp, pl.C, rr, ch, cwm[(size_t)grow * pl.C + ch]);
+            }
+    }
+}
+
+static int32_t check_weights(const wn_config& c, const wn_weights* w) {
+    if (!w || !w->first_w || !w->first_b || !w->last_a_w || !w->last_a_b || !w->last_b_w || !w->last_b_b || !w->layers)
+        return fail(WN_ERR_INVALID, "wn_weights: missing tensor");
+    for (int l = 0; l < c.layers; ++l) {
+        const wn_layer_weights& lw = w->layers[l];
+        if (!lw.conv_w || !lw.conv_b || !lw.out_w || !lw.out_b || !lw.skip_w || !lw.skip_b)
+            return fail(WN_ERR_INVALID, "wn_weights: missing layer tensor");
+        if (c.cin_channels > 0 && !lw.cond_w) return fail(WN_ERR_INVALID, "wn_weights: cond_w required (cin_channels > 0)");
+        if (c.gin_channels > 0 && !lw.gcond_w) return fail(WN_ERR_INVALID, "wn_weights: gcond_w required (gin_channels > 0)");
+    }
+    return WN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct WnHandle {
+    wn_config cfg;
+    int num_sms = 0;
+    long long smem_cap = 0;
+    bool have_weights = false;
+    WnPlan base;                  // plan for BT=1 (partition + blob layout are batch independent)
+    std::vector<int> ringtab;
+    float *d_wpack = nullptr, *d_cwpack = nullptr, *d_wg = nullptr, *d_first_w = nullptr, *d_first_b = nullptr;
+    int* d_ringtab = nullptr;
+    int* d_err = nullptr;
+    uint2* d_xbuf = nullptr;   size_t xbuf_bytes = 0;
+    float* d_ring = nullptr;   size_t ring_bytes = 0;
+    float* d_gbias = nullptr;  size_t gbias_bytes = 0;
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;   // wn_generate_host staging
+    cudaStream_t last_stream = nullptr;
+    bool pending = false;
+    int64_t launches = 0;
+    bool attr_set[4] = {false, false, false, false};
+};
+
+template <typename T>
+static int32_t ensure(T** ptr, size_t* have, size_t need) {
+    if (*have >= need && *ptr) return WN_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *have = 0;
+    CUDA_TRY(cudaMalloc((void**)ptr, need));
+    *have = need;
+    return WN_OK;
+}
+
+static int bt_index(int BT) { return BT == 1 ? 0 : BT == 2 ? 1 : BT == 4 ? 2 : 3; }
+
+static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
+    WnPlan pl;
+    std::vector<int> rt;
+    int32_t rc = build_plan(h->cfg, Bc, h->num_sms, h->smem_cap, pl, rt);
+    if (rc) return rc;
+    if (pl.P != h->base.P || pl.lb_floats != h->base.lb_floats)
+        return fail(WN_ERR_STATE, "plan changed between weight upload and generate");
+    const int BT = pl.BT;
+    const wn_config& c = h->cfg;
+
+    // exchange replicas: zeroed every call so stale tags can never match
+    const size_t xb = (size_t)pl.ncopy * pl.copy_stride_pairs * sizeof(uint2);
+    rc = ensure(&h->d_xbuf, &h->xbuf_bytes, xb);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_xbuf, 0, xb, st));
+    if (!pl.ring_in_smem) {
+        const size_t rb = std::max<size_t>(16, (size_t)pl.P * pl.ring_pos_total * pl.RA4 * BT * sizeof(float));
+        rc = ensure(&h->d_ring, &h->ring_bytes, rb);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->d_ring, 0, rb, st));
+    }
+    WnPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    if (c.gin_channels > 0) {
+        if (!a->g) return fail(WN_ERR_INVALID, "g is required (gin_channels > 0), cf. train.py:72-80 sanity_check");
+        const size_t gb = (size_t)Bc * pl.L * pl.G * sizeof(float);
+        rc = ensure(&h->d_gbias, &h->gbias_bytes, gb);
+        if (rc) return rc;
+        wn::wn_gbias_kernel<<<dim3(pl.L, Bc), 128, 0, st>>>(h->d_wg, a->g + (size_t)b0 * c.gin_channels, h->d_gbias,
+                                                          pl.L, pl.G, c.gin_channels);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        pp.gbias = h->d_gbias;
+    }
+    const int T = a->T, Tt = a->T_test, O = pl.O, K = pl.Kmix;
+    pp.wpack = h->d_wpack;
+    pp.cwpack = h->d_cwpack;
+    pp.first_w = h->d_first_w;
+    pp.first_b = h->d_first_b;
+    pp.xbuf = h->d_xbuf;
+    pp.ring_g = h->d_ring;
+    pp.ringtab = h->d_ringtab;
+    pp.err = h->d_err;
+    pp.c = a->c ? a->c + (size_t)b0 * T * pl.C : nullptr;
+    pp.initial = a->initial ? a->initial + b0 : nullptr;
+    pp.test_scalar = a->test_scalar ? a->test_scalar + (size_t)b0 * Tt : nullptr;
+    pp.test_index = a->test_index ? a->test_index + (size_t)b0 * Tt : nullptr;
+    pp.test_dense = a->test_dense ? a->test_dense + (size_t)b0 * Tt * O : nullptr;
+    // noise is (T, Btotal, .): the kernel indexes with the total batch, so shift by the row
+    pp.u1 = a->noise_u1 ? a->noise_u1 + (size_t)b0 * K : nullptr;
+    pp.u2 = a->noise_u2 ? a->noise_u2 + b0 : nullptr;
+    pp.z = a->noise_z ? a->noise_z + b0 : nullptr;
+    pp.e = a->noise_e ? a->noise_e + (size_t)b0 * O : nullptr;
+    pp.out_scalar = a->out_scalar ? a->out_scalar + (size_t)b0 * T : nullptr;
+    pp.out_index = a->out_index ? a->out_index + (size_t)b0 * T : nullptr;
+    pp.out_dense = a->out_dense ? a->out_dense + (size_t)b0 * O * T : nullptr;
+    pp.params_out = a->params_out ? a->params_out + (size_t)b0 * O * T : nullptr;
+    pp.B = Bc;
+    pp.Btot = a->B;
+    pp.b0 = b0;
+    pp.T = T;
+    pp.T_test = Tt;
+    pp.initial_index = a->initial_index < 0 ? 127 : a->initial_index;   // wavenet.py:286
+    pp.flags = a->flags;
+    pp.noise_kind = a->noise_kind;
+    pp.seed = a->seed;
+    pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
+
+    void* kargs[2] = {(void*)&pl, (void*)&pp};
+    const void* fn = nullptr;
+    switch (BT) {
+        case 1: fn = (const void*)wn::wn_persistent_kernel<1>; break;
+        case 2: fn = (const void*)wn::wn_persistent_kernel<2>; break;
+        case 4: fn = (const void*)wn::wn_persistent_kernel<4>; break;
+        default: fn = (const void*)wn::wn_persistent_kernel<8>; break;
+    }
+    if (!h->attr_set[bt_index(BT)]) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
+        h->attr_set[bt_index(BT)] = true;
+    }
+    // cooperative launch: the runtime refuses to start unless all P blocks are co-resident,
+    // which the spin-wait exchanges require
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pl.P), dim3(WN_NTHREADS), kargs, (size_t)pl.smem_bytes, st));
+    h->launches++;
+    return WN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t wn_abi_version(void) { return WN_ABI_VERSION; }
+const char* wn_last_error(void) { return g_err.c_str(); }
+
+int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, wn_plan_info* out) {
+    if (!cfg || !out) return fail(WN_ERR_INVALID, "null argument");
+    WnPlan pl;
+    std::vector<int> rt;
+    int32_t rc = build_plan(*cfg, batch, num_sms, smem_per_cta, pl, rt);
+    if (rc) return rc;
+    fill_info(*cfg, pl, out);
+    return WN_OK;
+}
+
+int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, const wn_weights* w,
+                    int32_t cta, float* packed, int64_t packed_floats) {
+    if (!cfg || !packed) return fail(WN_ERR_INVALID, "null argument");
+    WnPlan pl;
+    std::vector<int> rt;
+    int32_t rc = build_plan(*cfg, batch, num_sms, smem_per_cta, pl, rt);
+    if (rc) return rc;
+    rc = check_weights(*cfg, w);
+    if (rc) return rc;
+    if (cta < 0 || cta >= pl.P) return fail(WN_ERR_INVALID, "cta out of range");
+    if (packed_floats < pl.cta_w_floats) return fail(WN_ERR_INVALID, "packed buffer too small");
+    pack_cta(pl, *w, cta, packed);
+    if (packed_floats >= pl.cta_w_floats + pl.cta_cw_floats) pack_cw_cta(pl, *w, cta, packed + pl.cta_w_floats);
+    return WN_OK;
+}
+
+int32_t wn_create(const wn_config* cfg, void** handle) {
+    if (!cfg || !handle) return fail(WN_ERR_INVALID, "null argument");
+    *handle = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(WN_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (libwn has no CPU path; it needs an sm_100 GPU)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(WN_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(WN_ERR_CUDA, "libwn.so is built for sm_100a only; found compute capability " +
+                                     std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+    if (!coop) return fail(WN_ERR_CUDA, "device does not support cooperative launch");
+    WnHandle* h = new WnHandle();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_cap = (long long)prop.sharedMemPerBlockOptin;
+    int32_t rc = build_plan(h->cfg, 1, h->num_sms, h->smem_cap, h->base, h->ringtab);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    h->cfg.num_ctas = h->base.P;          // freeze the partition so every batch tile agrees with the packing
+    h->cfg.exchange_copies = h->base.ncopy;
+    if (cudaMalloc((void**)&h->d_err, 16) != cudaSuccess || cudaMemset(h->d_err, 0, 16) != cudaSuccess) {
+        delete h;
+        return fail(WN_ERR_CUDA, "cudaMalloc failed");
+    }
+    *handle = h;
+    return WN_OK;
+}
+
+int32_t wn_destroy(void* handle) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return WN_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(h->d_wpack); cudaFree(h->d_cwpack); cudaFree(h->d_wg); cudaFree(h->d_first_w); cudaFree(h->d_first_b);
+    cudaFree(h->d_ringtab); cudaFree(h->d_err); cudaFree(h->d_xbuf); cudaFree(h->d_ring); cudaFree(h->d_gbias);
+    cudaFree(h->d_scratch);
+    delete h;
+    return WN_OK;
+}
+
+int32_t wn_load_weights(void* handle, const wn_weights* w) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return fail(WN_ERR_INVALID, "null handle");
+    int32_t rc = check_weights(h->cfg, w);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const WnPlan& pl = h->base;
+    const wn_config& c = h->cfg;
+    auto upload = [&](float** dst, const std::vector<float>& src) -> int32_t {
+        if (*dst) cudaFree(*dst);
+        *dst = nullptr;
+        CUDA_TRY(cudaMalloc((void**)dst, std::max<size_t>(16, src.size() * sizeof(float))));
+        if (!src.empty()) CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return WN_OK;
+    };
+    std::vector<float> img((size_t)pl.P * pl.cta_w_floats);
+    for (int p = 0; p < pl.P; ++p) pack_cta(pl, *w, p, img.data() + (size_t)p * pl.cta_w_floats);
+    if ((rc = upload(&h->d_wpack, img))) return rc;
+    std::vector<float> cw((size_t)pl.P * pl.cta_cw_floats);
+    for (int p = 0; p < pl.P; ++p) pack_cw_cta(pl, *w, p, cw.data() + (size_t)p * pl.cta_cw_floats);
+    if ((rc = upload(&h->d_cwpack, cw))) return rc;
+    std::vector<float> wg;
+    if (c.gin_channels > 0) {
+        wg.resize((size_t)pl.L * pl.G * c.gin_channels);
+        for (int l = 0; l < pl.L; ++l)
+            memcpy(wg.data() + (size_t)l * pl.G * c.gin_channels, w->layers[l].gcond_w,
+                   (size_t)pl.G * c.gin_channels * sizeof(float));
+    }
+    if ((rc = upload(&h->d_wg, wg))) return rc;
+    std::vector<float> fw;
+    if (c.input_kind == WN_INPUT_SCALAR) {
+        fw.assign(w->first_w, w->first_w + pl.R);
+    } else {   // (R,O) -> [O][R]: a one-hot input selects one contiguous column
+        fw.resize((size_t)pl.O * pl.R);
+        for (int r = 0; r < pl.R; ++r)
+            for (int o = 0; o < pl.O; ++o) fw[(size_t)o * pl.R + r] = w->first_w[(size_t)r * pl.O + o];
+    }
+    if ((rc = upload(&h->d_first_w, fw))) return rc;
+    std::vector<float> fb(w->first_b, w->first_b + pl.R);
+    if ((rc = upload(&h->d_first_b, fb))) return rc;
+    if (h->d_ringtab) cudaFree(h->d_ringtab);
+    h->d_ringtab = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_ringtab, std::max<size_t>(16, h->ringtab.size() * sizeof(int))));
+    if (!h->ringtab.empty())
+        CUDA_TRY(cudaMemcpy(h->d_ringtab, h->ringtab.data(), h->ringtab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->have_weights = true;
+    return WN_OK;
+}
+
+static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
+    const wn_config& c = h->cfg;
+    if (!a) return fail(WN_ERR_INVALID, "null args");
+    if (a->B < 1 || a->T < 1) return fail(WN_ERR_INVALID, "B and T must be >= 1");
+    if ((long long)a->T * (2LL * c.layers + 3) >= 0xFFFFFFF0LL) return fail(WN_ERR_INVALID, "T too large for 32-bit tags");
+    if (c.cin_channels > 0 && !a->c) return fail(WN_ERR_INVALID, "c is required (cin_channels > 0), cf. train.py:82-87");
+    if (c.cin_channels == 0 && a->c) return fail(WN_ERR_INVALID, "c given but the model has no local conditioning");
+    if (c.gin_channels == 0 && a->g) return fail(WN_ERR_INVALID, "g given but the model has no global conditioning");
+    if (a->T_test < 0 || a->T_test > a->T) return fail(WN_ERR_INVALID, "T_test must be in [0,T] (wavenet.py:258)");
+    if (c.input_kind == WN_INPUT_SCALAR) {
+        if (!a->out_scalar) return fail(WN_ERR_INVALID, "out_scalar required");
+        if (a->T_test > 0 && !a->test_scalar) return fail(WN_ERR_INVALID, "test_scalar required when T_test > 0");
+    } else {
+        const bool quant = (a->flags & WN_FLAG_QUANTIZE) != 0, soft = (a->flags & WN_FLAG_SOFTMAX) != 0;
+        if (quant && !soft)
+            return fail(WN_ERR_INVALID, "quantize without softmax feeds logits to OneHotCategorical (wavenet.py:332-335): unsupported");
+        if (quant && !a->out_index) return fail(WN_ERR_INVALID, "out_index required with QUANTIZE");
+        if (!quant && !a->out_dense) return fail(WN_ERR_INVALID, "out_dense required without QUANTIZE");
+        if (a->T_test > 0 && !a->test_index && !a->test_dense) return fail(WN_ERR_INVALID, "test_index or test_dense required when T_test > 0");
+        if (a->initial_index >= c.out_channels) return fail(WN_ERR_INVALID, "initial_index out of range");
+    }
+    if (a->noise_kind == WN_NOISE_REPLAY) {
+        const bool quant = (a->flags & WN_FLAG_QUANTIZE) != 0;
+        if (c.head_kind == WN_HEAD_MOL && (!a->noise_u1 || !a->noise_u2)) return fail(WN_ERR_INVALID, "replay noise u1,u2 required (MoL)");
+        if (c.head_kind == WN_HEAD_GAUSS && !a->noise_z) return fail(WN_ERR_INVALID, "replay noise z required (Gaussian)");
+        if (c.head_kind == WN_HEAD_GAUSS && c.out_channels > 3 && !a->noise_u1) return fail(WN_ERR_INVALID, "replay noise u1 required (Gaussian mixture)");
+        if (c.head_kind == WN_HEAD_SOFTMAX && quant && !a->noise_e) return fail(WN_ERR_INVALID, "replay noise e required (softmax)");
+    } else if (a->noise_kind != WN_NOISE_PHILOX)
+        return fail(WN_ERR_INVALID, "bad noise_kind");
+    return WN_OK;
+}
+
+int32_t wn_generate(void* handle, const wn_generate_args* a) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return fail(WN_ERR_INVALID, "null handle");
+    if (!h->have_weights) return fail(WN_ERR_STATE, "wn_generate before wn_load_weights");
+    int32_t rc = validate_args(h, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)a->stream;
+    for (int b0 = 0; b0 < a->B; b0 += WN_MAX_BT) {
+        const int Bc = std::min(WN_MAX_BT, a->B - b0);
+        rc = launch_chunk(h, a, b0, Bc, st);
+        if (rc) return rc;
+    }
+    h->last_stream = st;
+    h->pending = true;
+    return WN_OK;
+}
+
+int32_t wn_sync(void* handle) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return fail(WN_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+    h->pending = false;
+    int err[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpy(err, h->d_err, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err[0] != 0) {
+        cudaMemset(h->d_err, 0, sizeof(err));
+        char buf[160];
+        snprintf(buf, sizeof(buf), "device watchdog: block %d thread %d stuck waiting on 0x%08x", err[2], err[3],
+                 (unsigned)err[1]);
+        return fail(WN_ERR_DEVICE, buf);
+    }
+    return WN_OK;
+}
+
+int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h || !out) return fail(WN_ERR_INVALID, "null argument");
+    WnPlan pl;
+    std::vector<int> rt;
+    int32_t rc = build_plan(h->cfg, std::min(batch, WN_MAX_BT), h->num_sms, h->smem_cap, pl, rt);
+    if (rc) return rc;
+    fill_info(h->cfg, pl, out);
+    out->launches = h->launches;
+    return WN_OK;
+}
+
+// Host-buffer variant: stage inputs to the device, run, copy results back (synchronous).
+int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return fail(WN_ERR_INVALID, "null handle");
+    if (!h->have_weights) return fail(WN_ERR_STATE, "wn_generate_host before wn_load_weights");
+    int32_t rc = validate_args(h, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const wn_config& c = h->cfg;
+    const size_t B = a->B, T = a->T, O = c.out_channels, Tt = a->T_test;
+    const size_t K = (c.head_kind == WN_HEAD_SOFTMAX) ? 0 : (O == 2 ? 1 : O / 3);
+    struct Item { const void* src; void* dst_host; size_t bytes; size_t off; };
+    std::vector<Item> in, out;
+    size_t total = 0;
+    auto add = [&](std::vector<Item>& v, const void* src, void* dsth, size_t bytes) {
+        if ((!src && !dsth) || bytes == 0) return (size_t)-1;
+        total = (total + 255) / 256 * 256;
+        v.push_back({src, dsth, bytes, total});
+        total += bytes;
+        return v.back().off;
+    };
+    const size_t o_c = add(in, a->c, nullptr, B * T * (size_t)c.cin_channels * 4);
+    const size_t o_g = add(in, a->g, nullptr, B * (size_t)c.gin_channels * 4);
+    const size_t o_init = add(in, a->initial, nullptr, B * 4);
+    const size_t o_ts = add(in, a->test_scalar, nullptr, B * Tt * 4);
+    const size_t o_ti = add(in, a->test_index, nullptr, B * Tt * 4);
+    const size_t o_td = add(in, a->test_dense, nullptr, B * Tt * O * 4);
+    const size_t o_u1 = add(in, a->noise_u1, nullptr, T * B * K * 4);
+    const size_t o_u2 = add(in, a->noise_u2, nullptr, T * B * 4);
+    const size_t o_z = add(in, a->noise_z, nullptr, T * B * 4);
+    const size_t o_e = add(in, a->noise_e, nullptr, T * B * O * 4);
+    const size_t o_os = add(out, nullptr, a->out_scalar, B * T * 4);
+    const size_t o_oi = add(out, nullptr, a->out_index, B * T * 4);
+    const size_t o_od = add(out, nullptr, a->out_dense, B * O * T * 4);
+    const size_t o_po = add(out, nullptr, a->params_out, B * O * T * 4);
+    rc = ensure(&h->d_scratch, &h->scratch_bytes, total + 256);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    for (const Item& it : in) CUDA_TRY(cudaMemcpyAsync(base + it.off, it.src, it.bytes, cudaMemcpyHostToDevice, st));
+    wn_generate_args d = *a;
+    auto dp = [&](size_t off) -> char* { return off == (size_t)-1 ? nullptr : base + off; };
+    d.c = (const float*)dp(o_c);
+    d.g = (const float*)dp(o_g);
+    d.initial = (const float*)dp(o_init);
+    d.test_scalar = (const float*)dp(o_ts);
+    d.test_index = (const int32_t*)dp(o_ti);
+    d.test_dense = (const float*)dp(o_td);
+    d.noise_u1 = (const float*)dp(o_u1);
+    d.noise_u2 = (const float*)dp(o_u2);
+    d.noise_z = (const float*)dp(o_z);
+    d.noise_e = (const float*)dp(o_e);
+    d.out_scalar = (float*)dp(o_os);
+    d.out_index = (int32_t*)dp(o_oi);
+    d.out_dense = (float*)dp(o_od);
+    d.params_out = (float*)dp(o_po);
+    rc = wn_generate(handle, &d);
+    if (rc) return rc;
+    for (const Item& it : out) CUDA_TRY(cudaMemcpyAsync(it.dst_host, base + it.off, it.bytes, cudaMemcpyDeviceToHost, st));
+    return wn_sync(handle);
+}
+
+int32_t wn_sample_mol(const float* y_bot, int32_t B, int32_t O, int32_t T, const float* u1_tbk, const float* u2_tb,
+                      float* out_bt, void* stream) {
+    if (!y_bot || !u1_tbk || !u2_tb || !out_bt) return fail(WN_ERR_INVALID, "null argument");
+    if (O % 3 != 0) return fail(WN_ERR_INVALID, "out_channels % 3 != 0 (mixture.py:130)");
+    const int n = B * T;
+    wn::wn_sample_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y_bot, B, O, T, u1_tbk, u2_tb, out_bt, 0);
+    CUDA_TRY(cudaGetLastError());
+    return WN_OK;
+}
+
+int32_t wn_sample_gauss(const float* y_bot, int32_t B, int32_t O, int32_t T, const float* u1_tbk, const float* z_tb,
+                        float* out_bt, void* stream) {
+    if (!y_bot || !z_tb || !out_bt) return fail(WN_ERR_INVALID, "null argument");
+    if (O != 2 && O % 3 != 0) return fail(WN_ERR_INVALID, "out_channels must be 2 or a multiple of 3 (mixture.py:229-234)");
+    if (O > 3 && !u1_tbk) return fail(WN_ERR_INVALID, "u1 required for a mixture");
+    const int n = B * T;
+    wn::wn_sample_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y_bot, B, O, T, u1_tbk, z_tb, out_bt, 1);
+    CUDA_TRY(cudaGetLastError());
+    return WN_OK;
+}
+
+}  // extern "C"

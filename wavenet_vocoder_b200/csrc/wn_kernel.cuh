@@ -1,0 +1,972 @@
+// wn_kernel.cuh — the persistent sm_100a synthesis kernel.
+//
+// One launch == one WaveNet.incremental_forward() call (reference wavenet.py:215-343): the whole
+// T-step loop, including the sampler, runs on the device.  P thread blocks (one per SM,
+// cooperative launch) each own a fixed slice of the output rows of every matrix (wn_plan.h).
+//
+// Per generated sample, per layer l (modules.py:112-163, conv.py:17-46), a block does
+//   stage A: wait for x_l (R floats, broadcast through L2) -> its rows of the CURRENT tap of the
+//            dilated conv (+ bias + conditioning + the queued products of the older taps)
+//            -> tanh*sigmoid -> publish its slice of y_l.
+//            Deferred (off the critical path, done while y_l travels): the OLDER taps' products
+//            W[:, :, k<kw-1] . x_l(t), queued for steps t+d, t+2d (this replaces the reference's
+//            input shift register, conv.py:32-44, by a queue of OUTPUT partials that is private
+//            to the block and (kw-1)*d*rows long instead of (kw-1)*d*R).
+//   stage B: wait for y_l (G/2 floats) -> its rows of conv1x1_out -> residual, *sqrt(.5)
+//            -> publish its slice of x_{l+1}.  Deferred: its rows of conv1x1_skip, accumulated
+//            in layer order like wavenet.py:312.
+// then the head (wavenet.py:313-319) in two more stages and the sampler (mixture.py), which every
+// block evaluates redundantly from the same noise so no further broadcast is needed.
+//
+// Exchange protocol: every value travels as an 8-byte (value, tag) pair (tag = step*NE+id+1),
+// written with one 8-byte store and polled with 8/16-byte loads, so data and "ready" flag are
+// one atomic word: no fences, no separate barrier, one L2 write + one L2 read per hop.  Each
+// vector is written to `ncopy` replicas so that the P readers do not all hammer the same L2
+// slices.
+//
+// Weights: fp32, packed per block by the host ("blobs").  A dedicated warp streams the blobs
+// into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a ring
+// of slots, running ahead of the compute warps; blobs that fit stay resident for the whole call.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "wn_plan.h"
+
+struct WnPtrs {
+    const float* wpack;        // [P][cta_w_floats]
+    const float* cwpack;       // [P][cta_cw_floats]
+    const float* gbias;        // [B][L][G] = Wg_l . g_b   (NULL without global conditioning)
+    const float* first_w;      // scalar input: [R];  one-hot input: transposed [O][R]
+    const float* first_b;      // [R]
+    uint2* xbuf;               // exchange replicas
+    float* ring_g;             // [P][ring floats] when the history rings do not fit in smem
+    const int* ringtab;        // [L*(kw-1)*2] : (offset in positions, delay D)
+    int* err;                  // [4] device fault word, last tag, block, info
+    // ---- per call
+    const float* c;
+    const float* initial;
+    const float* test_scalar;
+    const int* test_index;
+    const float* test_dense;
+    const float* u1;
+    const float* u2;
+    const float* z;
+    const float* e;
+    float* out_scalar;
+    int* out_index;
+    float* out_dense;
+    float* params_out;
+    int B, Btot, b0, T, T_test, initial_index;   // B rows in this launch; noise is strided by Btot
+    unsigned flags;
+    int noise_kind;
+    unsigned long long seed;
+    long long timeout_cycles;
+};
+
+#define WN_FLAG_SOFTMAX_ 1u
+#define WN_FLAG_QUANTIZE_ 2u
+
+namespace wn {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_pair2(const uint2* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_pair(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ int ld_flag(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// named barrier over the WN_NT compute threads only (aux warps never join), OR-reducing a flag
+__device__ __forceinline__ bool bar_or(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, 1, %2, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "n"(WN_NT)
+        : "memory");
+    return r != 0;
+}
+
+template <int NV>
+__device__ __forceinline__ void reduce_scatter(float (&v)[NV], int lane) {
+    // butterfly over the 32 lanes; while more than one value is left each step also halves the
+    // value set, so NV values cost NV-1+... shuffles instead of 5*NV.  Afterwards v[0] of lane
+    // l is the warp-wide sum of value (l >> (5 - log2 NV)).
+    int n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float send = hi ? v[i] : v[i + n];
+                    const float keep = hi ? v[i + n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+}
+
+__host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+// Philox4x32-10 (counter-based; the same (seed, step, utterance, slot) gives the same draw in
+// every block, which is what lets all blocks sample redundantly)
+__device__ __forceinline__ uint4 philox4(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t r) {   // (0,1), then mapped like uniform_(1e-5, 1-1e-5)
+    const float u = ((r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return 1e-5f + u * (1.0f - 2e-5f);
+}
+
+
+// slow path of every spin loop: has another block faulted / have we waited too long?
+__device__ __noinline__ bool wn_check_abort(volatile int* s_abort, int* err, long long timeout, uint32_t what, int p,
+                                            long long& t0) {
+    if (*s_abort) return true;
+    if (ld_flag(err) != 0) {
+        *s_abort = 1;
+        return true;
+    }
+    const long long now = clock64();
+    if (t0 == 0) {
+        t0 = now;
+        return false;
+    }
+    if (now - t0 > timeout) {
+        if (atomicCAS(err, 0, 1) == 0) {
+            err[1] = (int)what;
+            err[2] = p;
+            err[3] = (int)threadIdx.x;
+        }
+        *s_abort = 1;
+        return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+template <int BT>
+struct Engine {
+    const WnPlan& pl;
+    const WnPtrs& pp;
+    unsigned char* sm;
+    int tid, warp, lane, p;
+    uint64_t *bar_full, *bar_empty, *bar_cfull, *bar_cempty;
+    volatile int* s_abort;
+    int* ringtab;
+    float *xs, *red1, *red2, *sb, *cond, *skipacc, *hs, *noise, *first, *slots;
+    volatile float* ring;
+    float* s_in;     // [BT] scalar feedback
+    int* s_idx;      // [BT] class feedback
+    float* s_dense;  // [BT][O] dense feedback (only without QUANTIZE)
+    bool dead;
+
+    __device__ Engine(const WnPlan& pl_, const WnPtrs& pp_, unsigned char* sm_)
+        : pl(pl_), pp(pp_), sm(sm_) {
+        tid = threadIdx.x;
+        warp = tid >> 5;
+        lane = tid & 31;
+        p = blockIdx.x;
+        const int nslots = pl.nres + pl.nring;
+        bar_full = reinterpret_cast<uint64_t*>(sm + pl.sm_bar);
+        bar_empty = bar_full + nslots;
+        bar_cfull = bar_empty + (pl.nring > 0 ? pl.nring : 1);
+        bar_cempty = bar_cfull + 2;
+        s_abort = reinterpret_cast<volatile int*>(sm + pl.sm_misc);
+        s_in = reinterpret_cast<float*>(sm + pl.sm_in);
+        s_idx = reinterpret_cast<int*>(s_in + BT);
+        s_dense = reinterpret_cast<float*>(s_idx + BT);
+        ringtab = reinterpret_cast<int*>(sm + pl.sm_ringtab);
+        xs = reinterpret_cast<float*>(sm + pl.sm_xs);
+        red1 = reinterpret_cast<float*>(sm + pl.sm_red1);
+        red2 = reinterpret_cast<float*>(sm + pl.sm_red2);
+        sb = reinterpret_cast<float*>(sm + pl.sm_sb);
+        cond = reinterpret_cast<float*>(sm + pl.sm_cond);
+        skipacc = reinterpret_cast<float*>(sm + pl.sm_skipacc);
+        hs = reinterpret_cast<float*>(sm + pl.sm_hs);
+        noise = reinterpret_cast<float*>(sm + pl.sm_noise);
+        first = reinterpret_cast<float*>(sm + pl.sm_first);
+        slots = reinterpret_cast<float*>(sm + pl.sm_slots);
+        if (pl.ring_in_smem)
+            ring = reinterpret_cast<volatile float*>(sm + pl.sm_ring);
+        else
+            ring = pp.ring_g + (size_t)p * pl.ring_pos_total * pl.RA4 * BT;
+        dead = false;
+    }
+
+    // ---- watchdog: a stuck wait sets the device fault word and makes every block unwind
+    __device__ __forceinline__ bool check_abort(uint32_t what, long long& t0) {
+        return wn_check_abort(s_abort, pp.err, pp.timeout_cycles, what, p, t0);
+    }
+    __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, uint32_t what) {
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (!mbar_try_wait(bar, parity)) {
+            if (((++spins) & 255u) == 0 && check_abort(what, t0)) return false;
+        }
+        return true;
+    }
+
+    // ---- wait for a broadcast vector: thread owns elements k = tid + j*WN_NT
+    template <int E>
+    __device__ __forceinline__ void poll_vec(const uint2* __restrict__ src, int K, uint32_t tag,
+                                             float (&x)[WN_MAXE][BT]) {
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (true) {
+            uint32_t bad = 0;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int k = tid + j * WN_NT;
+                if (k < K) {
+                    const uint2* s = src + (size_t)k * BT;
+                    if constexpr (BT == 1) {
+                        const uint2 v = ld_pair(s);
+                        x[j][0] = __uint_as_float(v.x);
+                        bad |= v.y ^ tag;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BT; b += 2) {
+                            const uint4 v = ld_pair2(s + b);
+                            x[j][b] = __uint_as_float(v.x);
+                            bad |= v.y ^ tag;
+                            x[j][b + 1] = __uint_as_float(v.z);
+                            bad |= v.w ^ tag;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+                }
+            }
+            if (bad == 0) return;
+            if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
+                dead = true;
+                return;
+            }
+        }
+    }
+    template <int E>
+    __device__ __forceinline__ void stash(float* dst, int K, const float (&x)[WN_MAXE][BT]) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = tid + j * WN_NT;
+            if (k < K) {
+#pragma unroll
+                for (int b = 0; b < BT; ++b) dst[k * BT + b] = x[j][b];
+            }
+        }
+    }
+
+    // ---- rows x vector for NQ row quads; partial sums of warp w land in red[v*NWARP + w]
+    template <int E>
+    __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K,
+                                         const float (&x)[WN_MAXE][BT], float* __restrict__ red) {
+        constexpr int NV = 4 * BT;
+        constexpr int M = ilog2c(NV);
+        for (int q = 0; q < NQ; ++q) {
+            float acc[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int k = tid + j * WN_NT;
+                if (k < K) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + ((size_t)q * K + k) * 4);
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        acc[0 * BT + b] = fmaf(w4.x, x[j][b], acc[0 * BT + b]);
+                        acc[1 * BT + b] = fmaf(w4.y, x[j][b], acc[1 * BT + b]);
+                        acc[2 * BT + b] = fmaf(w4.z, x[j][b], acc[2 * BT + b]);
+                        acc[3 * BT + b] = fmaf(w4.w, x[j][b], acc[3 * BT + b]);
+                    }
+                }
+            }
+            reduce_scatter<NV>(acc, lane);
+            if ((lane & ((32 >> M) - 1)) == 0)
+                red[(q * NV + (lane >> (5 - M))) * WN_NWARP + warp] = acc[0];
+        }
+    }
+    __device__ __forceinline__ float red_sum(const float* red, int rowidx, int b) const {
+        const int v = (rowidx >> 2) * (4 * BT) + (rowidx & 3) * BT + b;
+        const float4* r = reinterpret_cast<const float4*>(red + v * WN_NWARP);
+        const float4 a = r[0], c = r[1];
+        return ((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w));
+    }
+    __device__ __forceinline__ void publish(int elem_off, int row, int b, float v, uint32_t tag) {
+        uint2* dst = pp.xbuf + ((size_t)(elem_off + row) * BT + b);
+        for (int c = 0; c < pl.ncopy; ++c) st_pair(dst + (size_t)c * pl.copy_stride_pairs, v, tag);
+    }
+
+    // ---- weight slots
+    __device__ __forceinline__ const float* acquire_blob(int t, int i) {
+        int slot;
+        uint32_t par;
+        if (i < pl.nres) {
+            slot = i;
+            par = 0;
+        } else {
+            const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
+            slot = pl.nres + (int)(js % (uint32_t)pl.nring);
+            par = (js / (uint32_t)pl.nring) & 1u;
+        }
+        if (!wait_bar(&bar_full[slot], par, 0x80000000u | (uint32_t)i)) dead = true;
+        return slots + (size_t)slot * pl.slot_floats;
+    }
+    __device__ __forceinline__ void release_blob(int t, int i) {
+        if (i >= pl.nres) {
+            const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[js % (uint32_t)pl.nring]);
+        }
+    }
+
+    // ======================================================================================
+    // weight streaming warp
+    // ======================================================================================
+    __device__ void tma_loop() {
+        if (lane != 0) return;
+        const float* base = pp.wpack + (size_t)p * pl.cta_w_floats;
+        const uint32_t lbytes = (uint32_t)pl.lb_floats * 4u, hbytes = (uint32_t)pl.hb_floats * 4u;
+        for (int i = 0; i < pl.nres; ++i) {
+            const uint32_t bytes = (i < pl.L) ? lbytes : hbytes;
+            mbar_expect_tx(&bar_full[i], bytes);
+            bulk_g2s(slots + (size_t)i * pl.slot_floats, base + (size_t)i * pl.lb_floats, bytes, &bar_full[i]);
+        }
+        const int nstream = pl.nblobs - pl.nres;
+        if (nstream <= 0) return;
+        const uint32_t total = (uint32_t)pp.T * (uint32_t)nstream;
+        int i = pl.nres;
+        for (uint32_t js = 0; js < total; ++js) {
+            const uint32_t s = js % (uint32_t)pl.nring, u = js / (uint32_t)pl.nring;
+            if (u > 0) {
+                if (!wait_bar(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
+            }
+            const uint32_t bytes = (i < pl.L) ? lbytes : hbytes;
+            uint64_t* fb = &bar_full[pl.nres + s];
+            mbar_expect_tx(fb, bytes);
+            bulk_g2s(slots + (size_t)(pl.nres + s) * pl.slot_floats, base + (size_t)i * pl.lb_floats, bytes, fb);
+            if (++i == pl.nblobs) i = pl.nres;
+        }
+    }
+
+    // ======================================================================================
+    // conditioning warp: cond[t&1][l][row][b] = Wc_l[rows] . c_t  (modules.py:141-145), one step
+    // ahead of the compute warps; weights come straight from L2 (they are read once per step)
+    // ======================================================================================
+    __device__ void cond_loop() {
+        const int C = pl.C, L = pl.L, T = pp.T, B = pp.B;
+        constexpr int NV = 4 * BT;
+        constexpr int M = ilog2c(NV);
+        const float* cw = pp.cwpack + (size_t)p * pl.cta_cw_floats;
+        for (int t = 0; t < T; ++t) {
+            const int par = t & 1, u = t >> 1;
+            if (u > 0) {
+                if (!wait_bar(&bar_cempty[par], (u - 1) & 1u, 0x20000000u)) return;
+            }
+            float ct[BT][WN_MAX_CI];
+#pragma unroll
+            for (int b = 0; b < BT; ++b)
+#pragma unroll
+                for (int i = 0; i < WN_MAX_CI; ++i) {
+                    const int ch = lane + 32 * i;
+                    ct[b][i] = (b < B && ch < C) ? __ldg(pp.c + ((size_t)b * T + t) * C + ch) : 0.f;
+                }
+            float* dst = cond + (size_t)par * L * pl.RA4 * BT;
+            for (int l = 0; l < L; ++l) {
+                for (int q = 0; q < pl.NQ_A; ++q) {
+                    float acc[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+                    const float* wq = cw + ((size_t)(l * pl.NQ_A + q) * C) * 4;
+#pragma unroll
+                    for (int i = 0; i < WN_MAX_CI; ++i) {
+                        const int ch = lane + 32 * i;
+                        if (ch < C) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wq + (size_t)ch * 4));
+#pragma unroll
+                            for (int b = 0; b < BT; ++b) {
+                                acc[0 * BT + b] = fmaf(w4.x, ct[b][i], acc[0 * BT + b]);
+                                acc[1 * BT + b] = fmaf(w4.y, ct[b][i], acc[1 * BT + b]);
+                                acc[2 * BT + b] = fmaf(w4.z, ct[b][i], acc[2 * BT + b]);
+                                acc[3 * BT + b] = fmaf(w4.w, ct[b][i], acc[3 * BT + b]);
+                            }
+                        }
+                    }
+                    reduce_scatter<NV>(acc, lane);
+                    if ((lane & ((32 >> M) - 1)) == 0) {
+                        const int v = lane >> (5 - M);   // = row_in_quad*BT + b
+                        dst[((size_t)l * pl.RA4 + q * 4 + v / BT) * BT + (v % BT)] = acc[0];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_cfull[par]);
+        }
+    }
+
+    // ======================================================================================
+    // sampler (one warp per utterance; every block computes the same thing)
+    // ======================================================================================
+    __device__ __forceinline__ void warp_argmax(float& best, int& bi) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+    }
+    // noise for step t of utterance b into noise[b][*]; layout [u1(0..K-1) | u2 or z] or [e(0..O-1)]
+    __device__ void fetch_noise(int t, int b) {
+        float* nz = noise + (size_t)b * (pl.O + 2);
+        const int B = pp.Btot, K = pl.Kmix, O = pl.O;
+        const uint32_t ub = (uint32_t)(pp.b0 + b);
+        const bool replay = pp.noise_kind == 0;
+        const uint2 key = make_uint2((uint32_t)pp.seed, (uint32_t)(pp.seed >> 32));
+        if (b >= pp.B) {   // padding row of the batch tile: harmless constants
+            for (int i = lane; i < O + 2; i += 32) nz[i] = 0.5f;
+            return;
+        }
+        if (pl.head_kind == 2) {
+            for (int i = lane; i < O; i += 32) {
+                float e;
+                if (replay) e = pp.e ? __ldg(pp.e + ((size_t)t * B + b) * O + i) : 1.0f;
+                else {
+                    const uint4 r = philox4(make_uint4((uint32_t)t, ub, (uint32_t)i, 2u), key);
+                    e = -logf(u01(r.x));
+                }
+                nz[i] = e;
+            }
+            return;
+        }
+        const bool mix = (pl.head_kind == 0) || (K > 1);
+        if (mix) {
+            for (int i = lane; i < K; i += 32) {
+                float u;
+                if (replay) u = __ldg(pp.u1 + ((size_t)t * B + b) * K + i);
+                else u = u01(philox4(make_uint4((uint32_t)t, ub, (uint32_t)i, 0u), key).x);
+                nz[i] = u;
+            }
+        }
+        if (lane == 0) {
+            float v;
+            if (pl.head_kind == 0) {
+                if (replay) v = __ldg(pp.u2 + (size_t)t * B + b);
+                else v = u01(philox4(make_uint4((uint32_t)t, ub, 0u, 1u), key).x);
+            } else {
+                if (replay) v = __ldg(pp.z + (size_t)t * B + b);
+                else {
+                    const uint4 r = philox4(make_uint4((uint32_t)t, ub, 0u, 1u), key);
+                    v = sqrtf(-2.f * logf(u01(r.x))) * cospif(2.f * u01(r.y));   // Box-Muller
+                }
+            }
+            nz[K] = v;
+        }
+    }
+    // draw sample of utterance b from hs[:, b]; sets the feedback for step t+1 and writes outputs
+    __device__ void sample_utt(int t, int b) {
+        const int O = pl.O, K = pl.Kmix, T = pp.T;
+        const float* nz = noise + (size_t)b * (pl.O + 2);
+        const bool writer = (p == 0);
+        if (pl.head_kind == 2) {
+            const bool softmax = (pp.flags & WN_FLAG_SOFTMAX_) != 0, quant = (pp.flags & WN_FLAG_QUANTIZE_) != 0;
+            // F.softmax (wavenet.py:332): exp(h - max) / sum
+            if (softmax) {
+                float m = -INFINITY;
+                for (int i = lane; i < O; i += 32) m = fmaxf(m, hs[i * BT + b]);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                float s = 0.f;
+                for (int i = lane; i < O; i += 32) {
+                    const float e = expf(hs[i * BT + b] - m);
+                    hs[i * BT + b] = e;
+                    s += e;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                for (int i = lane; i < O; i += 32) hs[i * BT + b] = hs[i * BT + b] / s;
+            }
+            if (quant) {
+                // OneHotCategorical(p).sample() (wavenet.py:334-335): renormalise, argmax(p / Exp(1))
+                float sp = 0.f;
+                for (int i = lane; i < O; i += 32) sp += hs[i * BT + b];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, off);
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int i = lane; i < O; i += 32) {
+                    const float r = (hs[i * BT + b] / sp) / nz[i];
+                    if (r > best) {
+                        best = r;
+                        bi = i;
+                    }
+                }
+                warp_argmax(best, bi);
+                if (bi >= O) bi = 0;
+                if (lane == 0) {
+                    if (writer && b < pp.B) pp.out_index[(size_t)b * T + t] = bi;
+                    s_idx[b] = (t + 1 < pp.T_test && b < pp.B) ? (pp.test_index ? pp.test_index[(size_t)b * pp.T_test + t + 1] : -1)
+                                                               : bi;
+                }
+            } else {
+                for (int i = lane; i < O; i += 32) {
+                    const float v = hs[i * BT + b];
+                    if (writer && b < pp.B) pp.out_dense[((size_t)b * O + i) * T + t] = v;
+                    s_dense[b * O + i] = v;
+                }
+                if (lane == 0) s_idx[b] = -1;
+            }
+            // teacher forcing with dense rows overrides the feedback
+            if (t + 1 < pp.T_test && pp.test_dense != nullptr && b < pp.B) {
+                for (int i = lane; i < O; i += 32)
+                    s_dense[b * O + i] = pp.test_dense[((size_t)b * pp.T_test + t + 1) * O + i];
+                if (lane == 0) s_idx[b] = -1;
+            }
+            return;
+        }
+        // ---- scalar heads
+        float mean, ls;
+        const bool mix = (pl.head_kind == 0) || (K > 1);
+        if (mix) {
+            // Gumbel-max over the K mixture logits (mixture.py:138-140 / :247-249)
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < K; i += 32) {
+                const float g = hs[i * BT + b] - logf(-logf(nz[i]));
+                if (g > best) {
+                    best = g;
+                    bi = i;
+                }
+            }
+            warp_argmax(best, bi);
+            if (bi >= K) bi = 0;
+            mean = hs[(K + bi) * BT + b];        // mixture.py:143-146 one-hot select
+            ls = hs[(2 * K + bi) * BT + b];
+        } else if (O == 2) {
+            mean = hs[0 * BT + b];               // mixture.py:258-259
+            ls = hs[1 * BT + b];
+        } else {
+            mean = hs[1 * BT + b];               // mixture.py:260-261 (C == 3)
+            ls = hs[2 * BT + b];
+        }
+        float xv;
+        if (pl.head_kind == 0) {
+            const float u = nz[K];
+            // mixture.py:152  x = mu + exp(s) * (log u - log(1-u)); separate roundings as in torch
+            xv = __fadd_rn(mean, __fmul_rn(expf(ls), __fsub_rn(logf(u), logf(__fsub_rn(1.0f, u)))));
+        } else {
+            // mixture.py:265-267  Normal(mu, exp(s)).sample() == z * sigma + mu
+            xv = __fadd_rn(__fmul_rn(nz[K], expf(ls)), mean);
+        }
+        xv = fminf(fmaxf(xv, -1.0f), 1.0f);      // mixture.py:154 / :269
+        if (lane == 0) {
+            if (writer && b < pp.B) pp.out_scalar[(size_t)b * T + t] = xv;
+            s_in[b] = (t + 1 < pp.T_test && b < pp.B) ? pp.test_scalar[(size_t)b * pp.T_test + t + 1] : xv;
+        }
+    }
+
+    // ======================================================================================
+    // compute warps
+    // ======================================================================================
+    __device__ __forceinline__ static int efor(int K) { return K <= WN_NT ? 1 : (K <= 2 * WN_NT ? 2 : 4); }
+
+    template <int E>
+    __device__ __forceinline__ void make_x0(float (&x)[WN_MAXE][BT]) {
+        const int R = pl.R, O = pl.O;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = tid + j * WN_NT;
+#pragma unroll
+            for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+            if (k < R) {
+                if (pl.input_kind == 0) {
+                    // wavenet.py:308  first 1x1 conv on a scalar: w*x + b
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) x[j][b] = fmaf(first[k], s_in[b], first[R + k]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        const int idx = s_idx[b];
+                        if (idx >= 0) {
+                            // one-hot input: the GEMV is a column gather
+                            x[j][b] = __ldg(pp.first_w + (size_t)idx * R + k) + first[R + k];
+                        } else {
+                            float a = 0.f;
+                            for (int o = 0; o < O; ++o)
+                                a = fmaf(__ldg(pp.first_w + (size_t)o * R + k), s_dense[b * O + o], a);
+                            x[j][b] = a + first[R + k];
+                        }
+                    }
+                }
+            }
+        }
+        stash<E>(xs, R, x);
+    }
+
+#define WN_DISPATCH_E(EV, ...)                       \
+    switch (EV) {                                    \
+        case 1: { constexpr int E = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int E = 2; __VA_ARGS__; } break; \
+        default: { constexpr int E = 4; __VA_ARGS__; } break; \
+    }
+
+    __device__ void compute_loop() {
+        const int L = pl.L, R = pl.R, G2 = pl.G2, S = pl.S, O = pl.O, kw = pl.kw, T = pp.T;
+        const int P = pl.P;
+        int y0, ny, x0r, nx, s0, ns, a0, na, b0, nb;
+        wn_part(G2, P, p, y0, ny);
+        wn_part(R, P, p, x0r, nx);
+        wn_part(S, P, p, s0, ns);
+        wn_part(S, P, p, a0, na);
+        wn_part(O, P, p, b0, nb);
+        const int ER = efor(R), EG = efor(G2), ES = efor(S), EO = efor(O);
+        const uint2* xin = pp.xbuf + (size_t)(p % pl.ncopy) * pl.copy_stride_pairs;
+        const uint32_t NEID = 2u * L + 3u;
+        const int RA4 = pl.RA4;
+        const int fr = tid / BT, fb = tid % BT;              // finalizer role: (row, utterance)
+        const int dt = tid - WN_NT / 2;                       // deferred-finalizer index
+        const int dr = dt >= 0 ? dt / BT : 0, db = dt >= 0 ? dt % BT : 0;
+        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
+        float* red2A = red2;                                  // older-tap products of stage A
+        float* red2B = red2 + (size_t)pl.NQ_D * 4 * BT * WN_NWARP;   // skip rows of stage B
+        float x[WN_MAXE][BT];
+        float skipb_prev = 0.f;   // skip bias of the previous layer for this thread's deferred row
+
+        // feedback for step 0 (wavenet.py:281-301)
+        if (tid < BT) {
+            const int b = tid;
+            float v = 0.f;
+            int idx = -1;
+            if (b < pp.B) {
+                if (pl.input_kind == 0) {
+                    if (pp.T_test > 0) v = pp.test_scalar[(size_t)b * pp.T_test];
+                    else if (pp.initial) v = pp.initial[b];
+                } else {
+                    if (pp.T_test > 0) idx = pp.test_index ? pp.test_index[(size_t)b * pp.T_test] : -1;
+                    else idx = pp.initial_index;
+                }
+            } else if (pl.input_kind != 0) idx = 0;
+            s_in[b] = v;
+            s_idx[b] = idx;
+        }
+        if (pl.input_kind != 0 && pp.T_test > 0 && pp.test_dense != nullptr) {
+            for (int i = tid; i < BT * O; i += WN_NT) {
+                const int b = i / O, o = i % O;
+                s_dense[i] = (b < pp.B) ? pp.test_dense[((size_t)b * pp.T_test) * O + o] : 0.f;
+            }
+        }
+        if (bar_or(false)) return;
+
+        for (int t = 0; t < T; ++t) {
+            const uint32_t tagbase = (uint32_t)t * NEID + 1u;
+            if (pl.C > 0) {
+                if (!wait_bar(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
+            }
+            WN_DISPATCH_E(ER, make_x0<E>(x));
+            if (warp < BT) fetch_noise(t, warp);
+
+            for (int l = 0; l < L; ++l) {
+                const float* W = acquire_blob(t, l);
+                const bool last = (l == L - 1);
+                // ------------------------------------------------------------ stage A
+                // everything that does not depend on x_l(t) is summed before the wait
+                float pre_a = 0.f, pre_b = 0.f;
+                const bool finA = (tid < pl.NYm * BT) && (fr < ny);
+                if (finA) {
+                    const int ra = 2 * fr, rb = 2 * fr + 1;
+                    pre_a = sb[((size_t)l * RA4 + ra) * BT + fb];
+                    pre_b = sb[((size_t)l * RA4 + rb) * BT + fb];
+                    if (pl.C > 0) {
+                        const float* cd = cond + ((size_t)(t & 1) * L + l) * RA4 * BT;
+                        pre_a += cd[ra * BT + fb];
+                        pre_b += cd[rb * BT + fb];
+                    }
+                    for (int k = 0; k < kw - 1; ++k) {
+                        const int off = ringtab[(l * (kw - 1) + k) * 2], D = ringtab[(l * (kw - 1) + k) * 2 + 1];
+                        const volatile float* rp = ring + ((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT;
+                        pre_a += rp[ra * BT + fb];
+                        pre_b += rp[rb * BT + fb];
+                    }
+                }
+                if (l > 0) {
+                    const uint2* src = xin + (size_t)(pl.ex_x + l * R) * BT;
+                    WN_DISPATCH_E(ER, poll_vec<E>(src, R, tagbase + wn_eid_x(l), x); stash<E>(xs, R, x));
+                }
+                WN_DISPATCH_E(ER, gemv<E>(W + pl.lb_Acrit, pl.NQ_A, R, x, red1));
+                if (bar_or(dead)) return;                                            // S1
+                if (finA) {
+                    const float a = red_sum(red1, 2 * fr, fb) + pre_a;
+                    const float g = red_sum(red1, 2 * fr + 1, fb) + pre_b;
+                    const float yv = tanhf(a) * (1.0f / (1.0f + expf(-g)));            // modules.py:154
+                    publish(pl.ex_y + l * G2, y0 + fr, fb, yv, tagbase + wn_eid_y(l));
+                }
+                if (l > 0 && dt >= 0 && dt < pl.NSm * BT && dr < ns) {
+                    // deferred from layer l-1: its skip rows, accumulated in layer order (wavenet.py:312)
+                    const float h = red_sum(red2B, dr, db) + skipb_prev;
+                    skipacc[dr * BT + db] = (l == 1) ? h : skipacc[dr * BT + db] + h;
+                }
+                if (last && pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // cond[t&1] consumed
+                if (kw > 1) { WN_DISPATCH_E(ER, gemv<E>(W + pl.lb_Adef, pl.NQ_D, R, x, red2A)); }
+                // ------------------------------------------------------------ stage B
+                {
+                    const uint2* src = xin + (size_t)(pl.ex_y + l * G2) * BT;
+                    WN_DISPATCH_E(EG, poll_vec<E>(src, G2, tagbase + wn_eid_y(l), x));
+                }
+                if (!last) { WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bo, pl.NQ_BO, G2, x, red1)); }
+                else { WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bs, pl.NQ_BS, G2, x, red1)); }
+                if (bar_or(dead)) return;                                            // S2
+                if (!last) {
+                    if (tid < pl.NXm * BT && fr < nx) {
+                        // modules.py:160-162  (conv1x1_out(y) + residual) * sqrt(0.5)
+                        const float o = red_sum(red1, fr, fb) + W[pl.lb_outb + fr];
+                        const float xn = (o + xs[(x0r + fr) * BT + fb]) * RSQRT2;
+                        publish(pl.ex_x + (l + 1) * R, x0r + fr, fb, xn, tagbase + wn_eid_x(l + 1));
+                    }
+                } else {
+                    if (tid < pl.NSm * BT && fr < ns) {
+                        // last layer: its residual output is never used (wavenet.py:310-313); finish
+                        // the skip sum, scale by sqrt(1/L) and apply the first ReLU of the head
+                        const float h = red_sum(red1, fr, fb) + W[pl.lb_skipb + fr];
+                        const float tot = (L == 1) ? h : skipacc[fr * BT + fb] + h;
+                        const float sk = fmaxf(tot * pl.skip_scale, 0.f);
+                        publish(pl.ex_sk, s0 + fr, fb, sk, tagbase + wn_eid_sk(pl));
+                    }
+                }
+                if (kw > 1 && dt >= 0 && dt < (kw - 1) * pl.RA * BT) {
+                    // deferred from stage A: queue the older taps' products (conv.py:32-44 restated)
+                    const int tap = dr / pl.RA, rr = dr % pl.RA;
+                    const float v = red_sum(red2A, dr, db);
+                    const int off = ringtab[(l * (kw - 1) + tap) * 2], D = ringtab[(l * (kw - 1) + tap) * 2 + 1];
+                    ring[((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT + rr * BT + db] = v;
+                }
+                if (!last) {
+                    if (dt >= 0 && dt < pl.NSm * BT) skipb_prev = W[pl.lb_skipb + dr];
+                    WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bs, pl.NQ_BS, G2, x, red2B));
+                }
+                release_blob(t, l);
+            }
+            // ---------------------------------------------------------------- head (wavenet.py:313-319)
+            const float* H = acquire_blob(t, L);
+            if (na > 0) {
+                const uint2* src = xin + (size_t)pl.ex_sk * BT;
+                WN_DISPATCH_E(ES, poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), x);
+                              gemv<E>(H + pl.hb_Ha, pl.NQ_HA, S, x, red1));
+            }
+            if (bar_or(dead)) return;                                                // S3
+            if (tid < pl.NAm * BT && fr < na) {
+                const float h1 = fmaxf(red_sum(red1, fr, fb) + H[pl.hb_Hab + fr], 0.f);
+                publish(pl.ex_h1, a0 + fr, fb, h1, tagbase + wn_eid_h1(pl));
+            }
+            if (nb > 0) {
+                const uint2* src = xin + (size_t)pl.ex_h1 * BT;
+                WN_DISPATCH_E(ES, poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), x);
+                              gemv<E>(H + pl.hb_Hb, pl.NQ_HB, S, x, red1));
+            }
+            if (bar_or(dead)) return;                                                // S4
+            if (tid < pl.NBm * BT && fr < nb) {
+                const float h2 = red_sum(red1, fr, fb) + H[pl.hb_Hbb + fr];
+                publish(pl.ex_h2, b0 + fr, fb, h2, tagbase + wn_eid_h2(pl));
+            }
+            release_blob(t, L);
+            {
+                const uint2* src = xin + (size_t)pl.ex_h2 * BT;
+                WN_DISPATCH_E(EO, poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), x); stash<E>(hs, O, x));
+            }
+            if (bar_or(dead)) return;                                                // S5
+            if (p == 0 && pp.params_out != nullptr) {
+                for (int i = tid; i < O * BT; i += WN_NT) {
+                    const int o = i / BT, b = i % BT;
+                    if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
+                }
+                // the softmax sampler overwrites hs in place: finish the copy first (block-uniform)
+                if (pl.head_kind == 2) { if (bar_or(false)) return; }
+            }
+            if (warp < BT) sample_utt(t, warp);
+            if (bar_or(false)) return;                                               // S6
+        }
+    }
+};
+
+
+// ------------------------------------------------------------------------------------------
+// kernel entry
+// ------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(WN_NTHREADS, 1)
+wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ WnPtrs pp) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Engine<BT> eng(pl, pp, smem_raw);
+    const int tid = threadIdx.x, p = blockIdx.x;
+    const int nslots = pl.nres + pl.nring;
+    if (tid == 0) {
+        for (int i = 0; i < nslots; ++i) mbar_init(&eng.bar_full[i], 1);
+        for (int i = 0; i < pl.nring; ++i) mbar_init(&eng.bar_empty[i], WN_NWARP);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&eng.bar_cfull[i], 1);
+            mbar_init(&eng.bar_cempty[i], 1);
+        }
+        *eng.s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero the history (== the reference's zero-initialised queue, conv.py:35-36) and scratch
+    if (pl.ring_in_smem) {
+        const size_t n = (size_t)pl.ring_pos_total * pl.RA4 * BT;
+        for (size_t i = tid; i < n; i += WN_NTHREADS) eng.ring[i] = 0.f;
+    }
+    for (int i = tid; i < pl.NSm * BT; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
+    for (int i = tid; i < pl.L * (pl.kw - 1) * 2; i += WN_NTHREADS) eng.ringtab[i] = pp.ringtab[i];
+    for (int k = tid; k < pl.R; k += WN_NTHREADS) {
+        eng.first[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
+        eng.first[pl.R + k] = pp.first_b[k];
+    }
+    {
+        // static part of the pre-activation: conv bias + global-conditioning projection
+        // (modules.py:148-152 recomputes Wg.g every step although g is constant; fold it once)
+        int y0, ny;
+        wn_part(pl.G2, pl.P, p, y0, ny);
+        const float* blob0 = pp.wpack + (size_t)p * pl.cta_w_floats;
+        const int n = pl.L * pl.RA4 * BT;
+        for (int i = tid; i < n; i += WN_NTHREADS) {
+            const int b = i % BT, rr = (i / BT) % pl.RA4, l = i / (BT * pl.RA4);
+            float v = 0.f;
+            if (rr < pl.RA && (rr >> 1) < ny) {
+                v = blob0[(size_t)l * pl.lb_floats + pl.lb_convb + rr];
+                if (pp.gbias != nullptr && b < pp.B) {
+                    const int grow = (rr & 1) ? pl.G2 + y0 + (rr >> 1) : y0 + (rr >> 1);
+                    v += pp.gbias[((size_t)b * pl.L + l) * pl.G + grow];
+                }
+            }
+            eng.sb[i] = v;
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5;
+    if (warp == WN_NWARP) {
+        eng.tma_loop();
+        return;
+    }
+    if (warp == WN_NWARP + 1) {
+        if (pl.C > 0) eng.cond_loop();
+        return;
+    }
+    eng.compute_loop();
+}
+
+// gbias[b][l][row] = Wg_l[row,:] . g_b   (modules.py:148-152), once per call
+__global__ void wn_gbias_kernel(const float* __restrict__ wg, const float* __restrict__ g, float* __restrict__ out,
+                                int L, int G, int gin) {
+    const int l = blockIdx.x, b = blockIdx.y;
+    for (int row = threadIdx.x; row < G; row += blockDim.x) {
+        const float* w = wg + ((size_t)l * G + row) * gin;
+        float a = 0.f;
+        for (int i = 0; i < gin; ++i) a = fmaf(w[i], g[(size_t)b * gin + i], a);
+        out[((size_t)b * L + l) * G + row] = a;
+    }
+}
+
+// stand-alone samplers over (B,O,T): the reference's mixture.py entry points
+__global__ void wn_sample_kernel(const float* __restrict__ y, int B, int O, int T, const float* __restrict__ u1,
+                                 const float* __restrict__ n2, float* __restrict__ out, int gauss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int b = i / T, t = i % T;
+    const float* yb = y + (size_t)b * O * T + t;
+    float mean, ls;
+    const int K = (O == 2) ? 1 : O / 3;
+    if (K > 1 || (!gauss)) {
+        float best = -INFINITY;
+        int bi = 0;
+        for (int k = 0; k < K; ++k) {
+            const float gk = yb[(size_t)k * T] - logf(-logf(u1[((size_t)t * B + b) * K + k]));
+            if (gk > best) {
+                best = gk;
+                bi = k;
+            }
+        }
+        mean = yb[(size_t)(K + bi) * T];
+        ls = yb[(size_t)(2 * K + bi) * T];
+    } else if (O == 2) {
+        mean = yb[0];
+        ls = yb[(size_t)T];
+    } else {
+        mean = yb[(size_t)T];
+        ls = yb[(size_t)2 * T];
+    }
+    const float v = n2[(size_t)t * B + b];
+    float xv;
+    if (!gauss) xv = __fadd_rn(mean, __fmul_rn(expf(ls), __fsub_rn(logf(v), logf(__fsub_rn(1.0f, v)))));
+    else xv = __fadd_rn(__fmul_rn(v, expf(ls)), mean);
+    out[i] = fminf(fmaxf(xv, -1.0f), 1.0f);
+}
+
+}  // namespace wn

@@ -1,0 +1,89 @@
+// wn_plan.h — the execution plan shared by the host planner/packer and the persistent kernel.
+//
+// One generated sample is a chain of small matrix-vector "stages" with a strict serial
+// dependency (reference wavenet.py:296-336).  The engine spreads every stage over P cooperating
+// thread blocks (one per SM): block p owns a fixed slice of the OUTPUT rows of every matrix, so
+// its weights never move between SMs, and the stage outputs (a few hundred floats) are exchanged
+// through tagged slots in L2.  This header fixes (a) which rows a block owns, (b) the layout of
+// the per-block packed weight image ("blobs", one per layer plus one for the head), (c) the
+// shared-memory map, and (d) the exchange-slot map.  All of it is plain arithmetic on the model
+// shape so the host tests can check the packer without a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifndef WN_HD
+#ifdef __CUDACC__
+#define WN_HD __host__ __device__ __forceinline__
+#else
+#define WN_HD inline
+#endif
+#endif
+
+#define WN_NT 256                 // compute threads per block (8 warps)
+#define WN_NWARP (WN_NT / 32)
+#define WN_AUX_WARPS 2            // +1 weight-streaming (TMA) warp, +1 conditioning warp
+#define WN_NTHREADS (WN_NT + 32 * WN_AUX_WARPS)
+#define WN_MAXE 4                 // a stage input vector has at most WN_MAXE*WN_NT entries
+#define WN_MAX_BT 8               // utterances processed together by one launch
+#define WN_MAX_CI 4               // local-conditioning channels <= 32*WN_MAX_CI
+
+struct WnPlan {
+    // ---- model shape (wavenet.py:98-111)
+    int L, per_stack, R, G, G2, S, O, kw, C, gin, input_kind, head_kind, Kmix;
+    // ---- partition: P blocks; max rows a block owns in each matrix
+    int P;
+    int NYm;      // gate pairs (rows j and j+G/2 of the dilated conv, modules.py:138)
+    int NXm;      // rows of conv1x1_out  (modules.py:160)
+    int NSm;      // rows of conv1x1_skip (modules.py:157)
+    int NAm;      // rows of last_conv_layers[1]
+    int NBm;      // rows of last_conv_layers[3]
+    int RA;       // 2*NYm : rows of the dilated conv a block evaluates (a_j, b_j interleaved)
+    // row quads per group ("quad-major" layout [quad][k][4 rows], one 16-byte smem load feeds 4 rows)
+    int NQ_A, NQ_D, NQ_BO, NQ_BS, NQ_HA, NQ_HB;
+    // ---- layer blob, offsets in floats
+    int lb_Acrit;   // current tap  (k = kw-1): needed on the critical path
+    int lb_Adef;    // older taps   (k < kw-1): their products are queued for steps t+d, t+2d ...
+    int lb_convb;   // conv bias for the RA rows
+    int lb_Bo, lb_Bs, lb_outb, lb_skipb;
+    int lb_floats;
+    // ---- head blob
+    int hb_Ha, hb_Hab, hb_Hb, hb_Hbb, hb_floats;
+    int slot_floats;            // shared-memory slot size (>= both blobs)
+    long long cta_w_floats;     // packed floats per block = L*lb_floats + hb_floats
+    int nblobs;                 // L + 1 per step
+    int nres;                   // blobs [0,nres) stay resident in shared memory for the whole call
+    int nring;                  // the others stream through nring slots every step
+    // ---- conditioning weights (kept in L2, read by the conditioning warp): [L][NQ_A][C][4]
+    long long cta_cw_floats;
+    // ---- exchange: element offsets (multiply by BT for pairs) of each vector inside one copy
+    int NE;                     // exchanges per step = 2L+2 (tags use 2L+3 ids)
+    int ncopy;
+    int ex_x, ex_y, ex_sk, ex_h1, ex_h2, ex_elems;
+    long long copy_stride_pairs;
+    // ---- batch tile
+    int BT;
+    // ---- history rings of the older-tap products
+    int ring_in_smem;
+    long long ring_pos_total;   // sum over (layer, tap) of the delay; one position = RA4*BT floats
+    int RA4;                    // 4*NQ_A
+    // ---- shared memory map (byte offsets)
+    int sm_bar, sm_misc, sm_ringtab, sm_xs, sm_red1, sm_red2, sm_sb, sm_cond, sm_skipacc, sm_hs,
+        sm_noise, sm_in, sm_first, sm_ring, sm_slots, smem_bytes;
+    float skip_scale;           // sqrt(1/L), wavenet.py:313
+};
+
+// balanced split of `rows` over P blocks: block p owns [base, base+cnt)
+WN_HD void wn_part(int rows, int P, int p, int& base, int& cnt) {
+    int q = rows / P, r = rows % P;
+    base = p * q + (p < r ? p : r);
+    cnt = q + (p < r ? 1 : 0);
+}
+
+WN_HD int wn_ceil_div(int a, int b) { return (a + b - 1) / b; }
+WN_HD int wn_dilation(const WnPlan& pl, int l) { return 1 << (l % pl.per_stack); }
+// exchange ids within a step (tag = t*(2L+3) + id + 1)
+WN_HD int wn_eid_x(int l) { return 2 * l - 1; }      // input of layer l >= 1
+WN_HD int wn_eid_y(int l) { return 2 * l; }          // gated activation of layer l
+WN_HD int wn_eid_sk(const WnPlan& pl) { return 2 * pl.L; }
+WN_HD int wn_eid_h1(const WnPlan& pl) { return 2 * pl.L + 1; }
+WN_HD int wn_eid_h2(const WnPlan& pl) { return 2 * pl.L + 2; }
