@@ -82,7 +82,7 @@ def test_make_generation_fast_gives_same_result():
     assert float((y1 - y2).abs().max()) <= 1e-5
 
 
-@pytest.mark.parametrize("P", [1, 3, 8, 32])
+@pytest.mark.parametrize("P", [2, 3, 8, 32])
 def test_any_block_count_gives_same_head_outputs(P):
     """The row partition must not change the result beyond fp32 reassociation."""
     from wavenet_vocoder_b200.engine import SynthesisEngine
@@ -194,7 +194,7 @@ def test_philox_sampling_is_seed_reproducible_and_self_consistent():
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
     assert float(y1.abs().max()) <= 1.0 and float(y1.std()) > 1e-3
     ti = torch.cat([torch.zeros(gc.B, 1, 1, device="cuda"), y1[:, :, :-1]], dim=2)
-    y4 = m.incremental_forward(test_inputs=ti, c=c, T=gc.T, seed=None if False else 0)
+    y4 = m.incremental_forward(test_inputs=ti, c=c, T=gc.T, seed=0)
     torch.manual_seed(11)
     y5 = m.incremental_forward(test_inputs=ti, c=c, T=gc.T)
     assert torch.equal(y5, y1)

@@ -70,21 +70,23 @@ def test_plan_numbers_match_survey_table():
     assert p["flops_per_sample"] == 49299456
     assert p["weight_bytes_per_step"] == 4 * 24681246
     assert p["num_ctas"] == 128 and p["rows_y"] == 2 and p["rows_x"] == 4 and p["rows_skip"] == 2
-    assert p["exchanges_per_step"] == 50
+    assert p["exchanges_per_step"] == 27      # one broadcast per layer + skip + two head stages
     assert p["smem_bytes"] <= SMEM
     assert p["resident_blobs"] + p["ring_slots"] >= 3
-    # config 3 (14.67 MB) and config 1 (1.73 MB) fit entirely in shared memory: nothing streams
+    # config 1 (1.73 MB) fits entirely in shared memory: nothing streams.  Config 3 (14.67 MB of
+    # weights, +36% row-quad padding and the folded M matrices) keeps 17 of 25 blobs resident.
     cfg3 = make_config(layers=24, stacks=4, residual_channels=128, gate_channels=256, skip_out_channels=128,
                        out_channels=2, kernel_size=3, cin_channels=80, gin_channels=16, scalar_input=True,
                        output_distribution="Normal")
     p3 = plan_of(cfg3)
     assert p3["flops_per_sample"] == 7308032 + 2 * 24 * 256 * 0   # Wg.g is folded once per call
-    assert p3["ring_slots"] == 0 and p3["resident_blobs"] == 25 and p3["streamed_bytes_per_step"] == 0
+    assert p3["resident_blobs"] >= 16 and p3["smem_bytes"] <= SMEM
     cfg1 = make_config(layers=12, stacks=2, residual_channels=64, gate_channels=128, skip_out_channels=64,
                        out_channels=256, kernel_size=3, cin_channels=-1, gin_channels=-1, scalar_input=False,
                        output_distribution="Logistic")
     p1 = plan_of(cfg1)
     assert p1["flops_per_sample"] == 860160 and p1["num_ctas"] == 64
+    assert p1["ring_slots"] == 0 and p1["resident_blobs"] == 13 and p1["streamed_bytes_per_step"] == 0
     # config 5: 30 layers / 3 cycles, dilation up to 512
     cfg5 = make_config(layers=30, stacks=3, residual_channels=256, gate_channels=512, skip_out_channels=256,
                        out_channels=30, kernel_size=3, cin_channels=80, gin_channels=-1, scalar_input=True,
@@ -126,6 +128,10 @@ def unquad(grp, nq, K):
 
 
 class PackedModel:
+    """Reads the packed image back with its own arithmetic for the layout documented in
+    csrc/wn_plan.h: first blob [Zx | zb], layer blobs [Zy | Zx | Xo | Td | Sk | zb | xb | sb],
+    tail blob [Td | Sk | sb | Ha | Hab | Hb | Hbb]; every matrix group is [quad][k][4 rows]."""
+
     def __init__(self, gc, P):
         cfg = cfg_for(gc, num_ctas=P)
         self.gc, self.cfg = gc, cfg
@@ -142,42 +148,46 @@ class PackedModel:
         RA = 2 * NYm
         nqA, nqD = cdiv(RA, 4), cdiv((kw - 1) * RA, 4)
         nqBO, nqBS, nqHA, nqHB = cdiv(NXm, 4), cdiv(NSm, 4), cdiv(NAm, 4), cdiv(NBm, 4)
-        # layer blob: [Acrit | Adef | convb | Bo | Bs | outb | skipb], head: [Ha | Hab | Hb | Hbb]
-        sizes = [nqA * R * 4, nqD * R * 4, 4 * nqA, nqBO * G2 * 4, nqBS * G2 * 4, 4 * nqBO, 4 * nqBS]
-        offs = np.concatenate([[0], np.cumsum(sizes)])
-        lb = int(offs[-1])
-        assert info["layer_blob_bytes"] == 4 * lb
-        hsizes = [nqHA * S * 4, 4 * nqHA, nqHB * S * 4, 4 * nqHB]
-        hoffs = np.concatenate([[0], np.cumsum(hsizes)])
-        assert info["head_blob_bytes"] == 4 * int(hoffs[-1])
+
+        def offsets(sizes):
+            return [int(v) for v in np.concatenate([[0], np.cumsum(sizes)])]
+        fo = offsets([nqA * R * 4, 4 * nqA])
+        lo = offsets([nqA * G2 * 4, nqA * R * 4, nqBO * G2 * 4, nqD * R * 4, nqBS * G2 * 4, 4 * nqA, 4 * nqBO, 4 * nqBS])
+        to = offsets([nqD * R * 4, nqBS * G2 * 4, 4 * nqBS, nqHA * S * 4, 4 * nqHA, nqHB * S * 4, 4 * nqHB])
+        fb, lb, tb = fo[-1], lo[-1], to[-1]
+        assert info["layer_blob_bytes"] == 4 * lb and info["head_blob_bytes"] == 4 * tb
         nmain = info["packed_bytes_per_cta"] // 4
         ncond = info["cond_packed_bytes_per_cta"] // 4
-        assert nmain == L * lb + int(hoffs[-1]) and ncond == L * nqA * self.C * 4
+        assert nmain == fb + (L - 1) * lb + tb and ncond == L * nqA * self.C * 4
         w, keep = weights_struct(gc.sd, L, self.C, max(c.gin_channels, 0))
         self.blocks = []
         for p in range(P):
             buf = np.zeros(nmain + ncond, dtype=np.float32)
             N.check(N.lib().wn_pack_cta(C.byref(cfg), 1, NSM, SMEM, C.byref(w), p,
                                         buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size))
-            blk = dict(y=part(G2, P, p), x=part(R, P, p), s=part(S, P, p), a=part(S, P, p), b=part(O, P, p), layers=[])
-            for l in range(L):
-                b = buf[l * lb:(l + 1) * lb]
-                seg = [b[offs[i]:offs[i + 1]] for i in range(7)]
-                lay = dict(Acrit=unquad(seg[0], nqA, R), Adef=unquad(seg[1], nqD, R), convb=seg[2],
-                           Bo=unquad(seg[3], nqBO, G2), Bs=unquad(seg[4], nqBS, G2), outb=seg[5], skipb=seg[6])
-                if self.C:
-                    cw = buf[nmain + l * nqA * self.C * 4: nmain + (l + 1) * nqA * self.C * 4]
-                    lay["cond"] = unquad(cw, nqA, self.C)
-                blk["layers"].append(lay)
-            hb = buf[L * lb:nmain]
-            hseg = [hb[hoffs[i]:hoffs[i + 1]] for i in range(4)]
-            blk.update(Ha=unquad(hseg[0], nqHA, S), Hab=hseg[1], Hb=unquad(hseg[2], nqHB, S), Hbb=hseg[3])
+            blk = dict(y=part(G2, P, p), x=part(R, P, p), s=part(S, P, p), a=part(S, P, p), b=part(O, P, p), stages=[])
+            b0 = buf[:fb]
+            blk["stages"].append(dict(Zx=unquad(b0[fo[0]:fo[1]], nqA, R), zb=b0[fo[1]:fo[2]]))
+            for s_ in range(1, L):
+                b = buf[fb + (s_ - 1) * lb: fb + s_ * lb]
+                seg = [b[lo[i]:lo[i + 1]] for i in range(8)]
+                blk["stages"].append(dict(Zy=unquad(seg[0], nqA, G2), Zx=unquad(seg[1], nqA, R),
+                                          Xo=unquad(seg[2], nqBO, G2), Td=unquad(seg[3], nqD, R),
+                                          Sk=unquad(seg[4], nqBS, G2), zb=seg[5], xb=seg[6], sb=seg[7]))
+            tbuf = buf[fb + (L - 1) * lb: nmain]
+            seg = [tbuf[to[i]:to[i + 1]] for i in range(7)]
+            blk["tail"] = dict(Td=unquad(seg[0], nqD, R), Sk=unquad(seg[1], nqBS, G2), sb=seg[2],
+                               Ha=unquad(seg[3], nqHA, S), Hab=seg[4], Hb=unquad(seg[5], nqHB, S), Hbb=seg[6])
+            blk["cond"] = [unquad(buf[nmain + l * nqA * self.C * 4: nmain + (l + 1) * nqA * self.C * 4], nqA, self.C)
+                           for l in range(L)] if self.C else None
             self.blocks.append(blk)
         self.RA = RA
         del keep
 
     def run_teacher_forced(self, b):
-        """Replay the kernel's dataflow for utterance b of the golden case; returns (O,T) head outputs."""
+        """Replay the kernel's staged dataflow for utterance b; returns (O,T) head outputs.
+        Stage s evaluates layer s from (y_{s-1}, x_{s-1}) with conv1x1_out folded into its current
+        tap; the older taps' products and the skip rows of layer s-1 are computed one stage late."""
         gc, L, R, G2, S, O, kw, P, RA = self.gc, self.L, self.R, self.G2, self.S, self.O, self.kw, self.P, self.RA
         w = gc.w
         T = gc.T
@@ -193,51 +203,63 @@ class PackedModel:
         rings = [[{tap: np.zeros(((kw - 1 - tap) * dil[l], RA), np.float32) for tap in range(kw - 1)}
                   for l in range(L)] for _ in range(P)]
         out = np.zeros((O, T), np.float32)
+        rs2 = np.float32(math.sqrt(0.5))
+
+        def gate(p, blk, l, z_dyn, t):
+            y0, ny = blk["y"]
+            pre = blk["stages"][l]["zb"][:RA].copy()
+            if gb is not None:
+                for j in range(ny):
+                    pre[2 * j] += gb[l][y0 + j]
+                    pre[2 * j + 1] += gb[l][G2 + y0 + j]
+            if self.C:
+                pre += blk["cond"][l][:RA] @ c_up[b, :, t].numpy()
+            for tap in range(kw - 1):
+                pre += rings[p][l][tap][t % ((kw - 1 - tap) * dil[l])]
+            z = z_dyn + pre
+            return [(y0 + j, np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))) for j in range(ny)]
+
+        def queue_taps(p, Td, layer, xvec, t):
+            for tap in range(kw - 1):
+                D = (kw - 1 - tap) * dil[layer]
+                rings[p][layer][tap][t % D] = Td[tap * RA:(tap + 1) * RA] @ xvec
+
         for t in range(T):
-            x = first_w @ x_tf[:, t] + first_b
+            x_prev = first_w @ x_tf[:, t] + first_b                # x_0, known to every block
+            y_prev = np.zeros(G2, np.float32)
+            for p, blk in enumerate(self.blocks):                  # stage 0
+                for k, v in gate(p, blk, 0, blk["stages"][0]["Zx"][:RA] @ x_prev, t):
+                    y_prev[k] = v
             skipacc = [None] * P
-            for l in range(L):
-                y = np.zeros(G2, np.float32)
+            for s_ in range(1, L):
+                y_new = np.zeros(G2, np.float32)
+                x_new = np.zeros(R, np.float32)
                 for p, blk in enumerate(self.blocks):
-                    lay = blk["layers"][l]
-                    y0, ny = blk["y"]
-                    pre = lay["convb"][:RA].copy()
-                    if gb is not None:
-                        for j in range(ny):
-                            pre[2 * j] += gb[l][y0 + j]
-                            pre[2 * j + 1] += gb[l][G2 + y0 + j]
-                    if self.C:
-                        pre += lay["cond"][:RA] @ c_up[b, :, t].numpy()
-                    for tap in range(kw - 1):
-                        D = (kw - 1 - tap) * dil[l]
-                        pre += rings[p][l][tap][t % D]
-                    z = lay["Acrit"][:RA] @ x + pre
-                    for j in range(ny):
-                        y[y0 + j] = np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))
-                    for tap in range(kw - 1):                       # deferred: queue older-tap products
-                        D = (kw - 1 - tap) * dil[l]
-                        rings[p][l][tap][t % D] = lay["Adef"][tap * RA:(tap + 1) * RA] @ x
-                xn = np.zeros(R, np.float32)
-                for p, blk in enumerate(self.blocks):
-                    lay = blk["layers"][l]
+                    st = blk["stages"][s_]
+                    for k, v in gate(p, blk, s_, st["Zy"][:RA] @ y_prev + st["Zx"][:RA] @ x_prev, t):
+                        y_new[k] = v
                     x0, nx = blk["x"]
+                    x_new[x0:x0 + nx] = (st["Xo"][:nx] @ y_prev + st["xb"][:nx] + x_prev[x0:x0 + nx]) * rs2
+                    queue_taps(p, st["Td"], s_ - 1, x_prev, t)     # deferred
                     s0, ns = blk["s"]
-                    o = lay["Bo"][:nx] @ y + lay["outb"][:nx]
-                    xn[x0:x0 + nx] = (o + x[x0:x0 + nx]) * np.float32(math.sqrt(0.5))
-                    h = lay["Bs"][:ns] @ y + lay["skipb"][:ns]
-                    skipacc[p] = h if l == 0 else skipacc[p] + h
-                x = xn
+                    h = st["Sk"][:ns] @ y_prev + st["sb"][:ns]
+                    skipacc[p] = h if s_ == 1 else skipacc[p] + h
+                y_prev, x_prev = y_new, x_new
             sk = np.zeros(S, np.float32)
-            for p, blk in enumerate(self.blocks):
+            for p, blk in enumerate(self.blocks):                  # stage L
+                tl = blk["tail"]
                 s0, ns = blk["s"]
-                sk[s0:s0 + ns] = np.maximum(skipacc[p] * np.float32(math.sqrt(1.0 / L)), 0)
+                h = tl["Sk"][:ns] @ y_prev + tl["sb"][:ns]
+                tot = h if L == 1 else skipacc[p] + h
+                sk[s0:s0 + ns] = np.maximum(tot * np.float32(math.sqrt(1.0 / L)), 0)
+                queue_taps(p, tl["Td"], L - 1, x_prev, t)
             h1 = np.zeros(S, np.float32)
             for blk in self.blocks:
                 a0, na = blk["a"]
-                h1[a0:a0 + na] = np.maximum(blk["Ha"][:na] @ sk + blk["Hab"][:na], 0)
+                h1[a0:a0 + na] = np.maximum(blk["tail"]["Ha"][:na] @ sk + blk["tail"]["Hab"][:na], 0)
             for blk in self.blocks:
                 b0, nb = blk["b"]
-                out[b0:b0 + nb, t] = blk["Hb"][:nb] @ h1 + blk["Hbb"][:nb]
+                out[b0:b0 + nb, t] = blk["tail"]["Hb"][:nb] @ h1 + blk["tail"]["Hbb"][:nb]
         return out
 
 

@@ -113,40 +113,42 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.NQ_BS = wn_ceil_div(pl.NSm, 4);
     pl.NQ_HA = wn_ceil_div(pl.NAm, 4);
     pl.NQ_HB = wn_ceil_div(pl.NBm, 4);
-    const int half = WN_NT / 2;
-    if (pl.NYm * BT > half || pl.NXm * BT > half || pl.NSm * BT > half || pl.NAm * BT > half ||
-        pl.NBm * BT > half || (pl.kw - 1) * pl.RA * BT > half)
-        return fail(WN_ERR_INVALID, "too many rows per block for this batch tile (use more blocks)");
-
     // ---- blobs
     int o = 0;
-    pl.lb_Acrit = o; o += pl.NQ_A * pl.R * 4;
-    pl.lb_Adef = o;  o += pl.NQ_D * pl.R * 4;
-    pl.lb_convb = o; o += pl.RA4;
-    pl.lb_Bo = o;    o += pl.NQ_BO * pl.G2 * 4;
-    pl.lb_Bs = o;    o += pl.NQ_BS * pl.G2 * 4;
-    pl.lb_outb = o;  o += 4 * pl.NQ_BO;
-    pl.lb_skipb = o; o += 4 * pl.NQ_BS;
+    pl.fb_Zx = o; o += pl.NQ_A * pl.R * 4;
+    pl.fb_zb = o; o += pl.RA4;
+    pl.fb_floats = align_up(o, 4);
+    o = 0;
+    pl.lb_Zy = o; o += pl.NQ_A * pl.G2 * 4;
+    pl.lb_Zx = o; o += pl.NQ_A * pl.R * 4;
+    pl.lb_Xo = o; o += pl.NQ_BO * pl.G2 * 4;
+    pl.lb_Td = o; o += pl.NQ_D * pl.R * 4;
+    pl.lb_Sk = o; o += pl.NQ_BS * pl.G2 * 4;
+    pl.lb_zb = o; o += pl.RA4;
+    pl.lb_xb = o; o += 4 * pl.NQ_BO;
+    pl.lb_sb = o; o += 4 * pl.NQ_BS;
     pl.lb_floats = align_up(o, 4);
     o = 0;
-    pl.hb_Ha = o;  o += pl.NQ_HA * pl.S * 4;
-    pl.hb_Hab = o; o += 4 * pl.NQ_HA;
-    pl.hb_Hb = o;  o += pl.NQ_HB * pl.S * 4;
-    pl.hb_Hbb = o; o += 4 * pl.NQ_HB;
-    pl.hb_floats = align_up(o, 4);
-    pl.slot_floats = align_up(std::max(pl.lb_floats, pl.hb_floats), 32);
-    pl.cta_w_floats = (long long)pl.L * pl.lb_floats + pl.hb_floats;
+    pl.tb_Td = o;  o += pl.NQ_D * pl.R * 4;
+    pl.tb_Sk = o;  o += pl.NQ_BS * pl.G2 * 4;
+    pl.tb_sb = o;  o += 4 * pl.NQ_BS;
+    pl.tb_Ha = o;  o += pl.NQ_HA * pl.S * 4;
+    pl.tb_Hab = o; o += 4 * pl.NQ_HA;
+    pl.tb_Hb = o;  o += pl.NQ_HB * pl.S * 4;
+    pl.tb_Hbb = o; o += 4 * pl.NQ_HB;
+    pl.tb_floats = align_up(o, 4);
+    pl.slot_floats = align_up(std::max(pl.fb_floats, std::max(pl.L > 1 ? pl.lb_floats : 0, pl.tb_floats)), 32);
+    pl.cta_w_floats = (long long)pl.fb_floats + (long long)(pl.L - 1) * pl.lb_floats + pl.tb_floats;
     pl.nblobs = pl.L + 1;
     pl.cta_cw_floats = (long long)pl.L * pl.NQ_A * pl.C * 4;
 
     // ---- exchange map
-    pl.NE = 2 * pl.L + 2;
+    pl.NE = pl.L + 3;
     int nc = c.exchange_copies > 0 ? c.exchange_copies : env_int("WN_NCOPY", 0);
-    if (nc <= 0) nc = std::max(1, std::min(8, P / 16));
+    if (nc <= 0) nc = 1;
     pl.ncopy = std::min(nc, P);
-    pl.ex_x = 0;
-    pl.ex_y = pl.L * pl.R;
-    pl.ex_sk = pl.ex_y + pl.L * pl.G2;
+    pl.ex_yx = 0;
+    pl.ex_sk = pl.L * (pl.G2 + pl.R);
     pl.ex_h1 = pl.ex_sk + pl.S;
     pl.ex_h2 = pl.ex_h1 + pl.S;
     pl.ex_elems = pl.ex_h2 + pl.O;
@@ -180,12 +182,13 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
         pl.sm_ringtab = take((long long)ringtab.size() * 4 + 16, 16);
         pl.sm_xs = take((long long)pl.R * BT * 4, 16);
-        const int nq1 = std::max(std::max(pl.NQ_A, pl.NQ_BO), std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
+        const int nq1 = std::max(pl.NQ_A + pl.NQ_BO, std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
         pl.sm_red1 = take((long long)nq1 * 4 * BT * WN_NWARP * 4, 16);
-        pl.sm_red2 = take((long long)(pl.NQ_D + pl.NQ_BS) * 4 * BT * WN_NWARP * 4 + 16, 16);
+        pl.red2_floats = (pl.NQ_D + pl.NQ_BS) * 4 * BT * WN_NWARP + 4;
+        pl.sm_red2 = take(2LL * pl.red2_floats * 4, 16);      // two buffers, alternating by stage
         pl.sm_sb = take((long long)pl.L * pl.RA4 * BT * 4, 16);
         pl.sm_cond = take(pl.C > 0 ? 2LL * pl.L * pl.RA4 * BT * 4 : 16, 16);
-        pl.sm_skipacc = take((long long)pl.NSm * BT * 4 + 16, 16);
+        pl.sm_skipacc = take((long long)(pl.NSm * BT + 8 * pl.NQ_BS) * 4 + 16, 16);   // running skip sum + 2 bias stashes
         pl.sm_hs = take((long long)pl.O * BT * 4, 16);
         pl.sm_noise = take((long long)BT * (pl.O + 2) * 4, 16);
         pl.sm_first = take(2LL * pl.R * 4, 16);
@@ -239,7 +242,8 @@ static void fill_info(const wn_config& c, const WnPlan& pl, wn_plan_info* out) {
     out->rings_in_smem = pl.ring_in_smem;
     out->smem_bytes = pl.smem_bytes;
     out->layer_blob_bytes = (int64_t)pl.lb_floats * 4;
-    out->head_blob_bytes = (int64_t)pl.hb_floats * 4;
+    out->head_blob_bytes = (int64_t)pl.tb_floats * 4;
+    out->reserved[0] = (int64_t)pl.fb_floats * 4;   // first-blob bytes
     out->packed_bytes_per_cta = (int64_t)pl.cta_w_floats * 4;
     out->cond_packed_bytes_per_cta = (int64_t)pl.cta_cw_floats * 4;
     const int64_t cin0 = (c.input_kind == WN_INPUT_SCALAR) ? 1 : pl.O;
@@ -251,7 +255,7 @@ static void fill_info(const wn_config& c, const WnPlan& pl, wn_plan_info* out) {
     out->flops_per_sample = 2 * mac;
     out->weight_bytes_per_step = 4 * (mac + biases);
     int64_t streamed = 0;
-    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += (i < pl.L ? pl.lb_floats : pl.hb_floats) * 4LL;
+    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += wn_blob_floats(pl, i) * 4LL;
     out->streamed_bytes_per_step = streamed * pl.P;
 }
 
@@ -262,8 +266,52 @@ static inline void put_q(float* grp, int K, int rowidx, int k, float v) {
     grp[((size_t)(rowidx >> 2) * K + k) * 4 + (rowidx & 3)] = v;
 }
 
-// packed image of block `p`: L layer blobs then the head blob (all zero-padded)
-static void pack_cta(const WnPlan& pl, const wn_weights& w, int p, float* out) {
+// Host-side folding for the one-broadcast-per-layer schedule (done once per weight upload, fp64):
+//   V_l = sqrt(.5) * W_l[:, :, kw-1]                 (l >= 1; modules.py:162 scale moved into the weight)
+//   M_l = V_{l+1} . Wo_l          (G x G/2)         (conv1x1_out of layer l folded into layer l+1)
+//   zb_l = conv_b_l + V_l . bo_{l-1}
+struct Folded {
+    std::vector<std::vector<float>> V, M, zb;     // per layer (V[0] is the plain current tap)
+};
+
+static void fold_layers(const WnPlan& pl, const wn_weights& w, Folded& f) {
+    const int L = pl.L, G = pl.G, R = pl.R, G2 = pl.G2, kw = pl.kw;
+    const float rs2 = 0.70710678118654752440f;
+    f.V.assign(L, {});
+    f.M.assign(L, {});
+    f.zb.assign(L, {});
+    for (int l = 0; l < L; ++l) {
+        const wn_layer_weights& lw = w.layers[l];
+        f.V[l].resize((size_t)G * R);
+        for (int g = 0; g < G; ++g)
+            for (int r = 0; r < R; ++r) {
+                const float wv = lw.conv_w[(size_t)g * kw * R + (size_t)(kw - 1) * R + r];
+                f.V[l][(size_t)g * R + r] = (l == 0) ? wv : wv * rs2;
+            }
+        f.zb[l].resize(G);
+        for (int g = 0; g < G; ++g) f.zb[l][g] = lw.conv_b ? lw.conv_b[g] : 0.f;
+        if (l == 0) continue;
+        const wn_layer_weights& pw = w.layers[l - 1];
+        f.M[l - 1].resize((size_t)G * G2);
+        std::vector<double> acc(G2);
+        for (int g = 0; g < G; ++g) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            double bacc = 0.0;
+            const float* vrow = &f.V[l][(size_t)g * R];
+            for (int r = 0; r < R; ++r) {
+                const double v = vrow[r];
+                const float* orow = pw.out_w + (size_t)r * G2;
+                for (int j = 0; j < G2; ++j) acc[j] += v * (double)orow[j];
+                if (pw.out_b) bacc += v * (double)pw.out_b[r];
+            }
+            for (int j = 0; j < G2; ++j) f.M[l - 1][(size_t)g * G2 + j] = (float)acc[j];
+            f.zb[l][g] = (float)((double)f.zb[l][g] + bacc);
+        }
+    }
+}
+
+// packed image of block `p`: first blob, L-1 layer blobs, tail blob (all zero-padded)
+static void pack_cta(const WnPlan& pl, const wn_weights& w, const Folded& f, int p, float* out) {
     memset(out, 0, (size_t)pl.cta_w_floats * sizeof(float));
     int y0, ny, x0, nx, s0, ns, a0, na, b0, nb;
     wn_part(pl.G2, pl.P, p, y0, ny);
@@ -271,41 +319,58 @@ static void pack_cta(const WnPlan& pl, const wn_weights& w, int p, float* out) {
     wn_part(pl.S, pl.P, p, s0, ns);
     wn_part(pl.S, pl.P, p, a0, na);
     wn_part(pl.O, pl.P, p, b0, nb);
-    const int R = pl.R, G2 = pl.G2, kw = pl.kw, S = pl.S;
-    for (int l = 0; l < pl.L; ++l) {
-        const wn_layer_weights& lw = w.layers[l];
-        float* blob = out + (size_t)l * pl.lb_floats;
-        for (int j = 0; j < ny; ++j)
-            for (int ab = 0; ab < 2; ++ab) {
-                const int rr = 2 * j + ab;                       // a_j, b_j interleaved
-                const int grow = ab ? G2 + y0 + j : y0 + j;      // modules.py:138 split
-                const float* row = lw.conv_w + (size_t)grow * kw * R;   // conv.py:56-61: col = k*R + r
-                for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Acrit, R, rr, k, row[(size_t)(kw - 1) * R + k]);
-                for (int tap = 0; tap < kw - 1; ++tap)
-                    for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Adef, R, tap * pl.RA + rr, k, row[(size_t)tap * R + k]);
-                blob[pl.lb_convb + rr] = lw.conv_b ? lw.conv_b[grow] : 0.f;
-            }
-        for (int r = 0; r < nx; ++r) {
-            const float* row = lw.out_w + (size_t)(x0 + r) * G2;
-            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Bo, G2, r, k, row[k]);
-            blob[pl.lb_outb + r] = lw.out_b ? lw.out_b[x0 + r] : 0.f;
-        }
+    const int R = pl.R, G2 = pl.G2, kw = pl.kw, S = pl.S, L = pl.L;
+    // the gate rows this block evaluates: a_j, b_j interleaved (modules.py:138 split)
+    auto grow = [&](int rr) { return (rr & 1) ? G2 + y0 + (rr >> 1) : y0 + (rr >> 1); };
+    auto pack_taps = [&](float* grp, int layer) {       // older taps of `layer` (conv.py:56-61: col = k*R + r)
+        const float* cw = w.layers[layer].conv_w;
+        for (int rr = 0; rr < 2 * ny; ++rr)
+            for (int tap = 0; tap < kw - 1; ++tap)
+                for (int k = 0; k < R; ++k)
+                    put_q(grp, R, tap * pl.RA + rr, k, cw[(size_t)grow(rr) * kw * R + (size_t)tap * R + k]);
+    };
+    auto pack_skip = [&](float* grp, float* bias, int layer) {
+        const wn_layer_weights& lw = w.layers[layer];
         for (int r = 0; r < ns; ++r) {
-            const float* row = lw.skip_w + (size_t)(s0 + r) * G2;
-            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Bs, G2, r, k, row[k]);
-            blob[pl.lb_skipb + r] = lw.skip_b ? lw.skip_b[s0 + r] : 0.f;
+            for (int k = 0; k < G2; ++k) put_q(grp, G2, r, k, lw.skip_w[(size_t)(s0 + r) * G2 + k]);
+            bias[r] = lw.skip_b ? lw.skip_b[s0 + r] : 0.f;
+        }
+    };
+    {   // stage 0
+        float* blob = out;
+        for (int rr = 0; rr < 2 * ny; ++rr) {
+            for (int k = 0; k < R; ++k) put_q(blob + pl.fb_Zx, R, rr, k, f.V[0][(size_t)grow(rr) * R + k]);
+            blob[pl.fb_zb + rr] = f.zb[0][grow(rr)];
         }
     }
-    float* hb = out + (size_t)pl.L * pl.lb_floats;
+    for (int s = 1; s < L; ++s) {
+        float* blob = out + wn_blob_off(pl, s);
+        const wn_layer_weights& pw = w.layers[s - 1];
+        for (int rr = 0; rr < 2 * ny; ++rr) {
+            const int g = grow(rr);
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Zy, G2, rr, k, f.M[s - 1][(size_t)g * G2 + k]);
+            for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Zx, R, rr, k, f.V[s][(size_t)g * R + k]);
+            blob[pl.lb_zb + rr] = f.zb[s][g];
+        }
+        for (int r = 0; r < nx; ++r) {
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Xo, G2, r, k, pw.out_w[(size_t)(x0 + r) * G2 + k]);
+            blob[pl.lb_xb + r] = pw.out_b ? pw.out_b[x0 + r] : 0.f;
+        }
+        pack_taps(blob + pl.lb_Td, s - 1);
+        pack_skip(blob + pl.lb_Sk, blob + pl.lb_sb, s - 1);
+    }
+    float* tb = out + wn_blob_off(pl, L);
+    pack_taps(tb + pl.tb_Td, L - 1);
+    pack_skip(tb + pl.tb_Sk, tb + pl.tb_sb, L - 1);
     for (int r = 0; r < na; ++r) {
         const float* row = w.last_a_w + (size_t)(a0 + r) * S;
-        for (int k = 0; k < S; ++k) put_q(hb + pl.hb_Ha, S, r, k, row[k]);
-        hb[pl.hb_Hab + r] = w.last_a_b ? w.last_a_b[a0 + r] : 0.f;
+        for (int k = 0; k < S; ++k) put_q(tb + pl.tb_Ha, S, r, k, row[k]);
+        tb[pl.tb_Hab + r] = w.last_a_b ? w.last_a_b[a0 + r] : 0.f;
     }
     for (int r = 0; r < nb; ++r) {
         const float* row = w.last_b_w + (size_t)(b0 + r) * S;
-        for (int k = 0; k < S; ++k) put_q(hb + pl.hb_Hb, S, r, k, row[k]);
-        hb[pl.hb_Hbb + r] = w.last_b_b ? w.last_b_b[b0 + r] : 0.f;
+        for (int k = 0; k < S; ++k) put_q(tb + pl.tb_Hb, S, r, k, row[k]);
+        tb[pl.tb_Hbb + r] = w.last_b_b ? w.last_b_b[b0 + r] : 0.f;
     }
 }
 
@@ -355,10 +420,11 @@ struct WnHandle {
     float* d_ring = nullptr;   size_t ring_bytes = 0;
     float* d_gbias = nullptr;  size_t gbias_bytes = 0;
     void* d_scratch = nullptr; size_t scratch_bytes = 0;   // wn_generate_host staging
+    long long* d_prof = nullptr; size_t prof_bytes = 0;    // WN_PROF=1 cycle counters
     cudaStream_t last_stream = nullptr;
     bool pending = false;
     int64_t launches = 0;
-    bool attr_set[4] = {false, false, false, false};
+    bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
 };
 
 template <typename T>
@@ -441,18 +507,36 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.noise_kind = a->noise_kind;
     pp.seed = a->seed;
     pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
+    pp.prof = nullptr;
+    if (env_int("WN_PROF", 0)) {
+        const size_t pb = (size_t)pl.P * 8 * sizeof(long long);
+        rc = ensure(&h->d_prof, &h->prof_bytes, pb);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, pb, st));
+        pp.prof = h->d_prof;
+    }
 
     void* kargs[2] = {(void*)&pl, (void*)&pp};
+    // kernel variants: <batch tile, elements of x per thread, elements of y per thread>
+    const int er = pl.R <= WN_NT ? 1 : (pl.R <= 2 * WN_NT ? 2 : 4);
+    const int eg = pl.G2 <= WN_NT ? 1 : (pl.G2 <= 2 * WN_NT ? 2 : 4);
+    const int var = (er == 1 && eg == 1) ? 0 : ((er <= 2 && eg == 1) ? 1 : 2);
     const void* fn = nullptr;
+#define WN_PICK(BT_)                                                                        \
+    fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 1, 1>                        \
+                  : (var == 1 ? (const void*)wn::wn_persistent_kernel<BT_, 2, 1>            \
+                              : (const void*)wn::wn_persistent_kernel<BT_, 4, 4>)
     switch (BT) {
-        case 1: fn = (const void*)wn::wn_persistent_kernel<1>; break;
-        case 2: fn = (const void*)wn::wn_persistent_kernel<2>; break;
-        case 4: fn = (const void*)wn::wn_persistent_kernel<4>; break;
-        default: fn = (const void*)wn::wn_persistent_kernel<8>; break;
+        case 1: WN_PICK(1); break;
+        case 2: WN_PICK(2); break;
+        case 4: WN_PICK(4); break;
+        default: WN_PICK(8); break;
     }
-    if (!h->attr_set[bt_index(BT)]) {
+#undef WN_PICK
+    const int ai = bt_index(BT) * 3 + var;
+    if (!h->attr_set[ai]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
-        h->attr_set[bt_index(BT)] = true;
+        h->attr_set[ai] = true;
     }
     // cooperative launch: the runtime refuses to start unless all P blocks are co-resident,
     // which the spin-wait exchanges require
@@ -490,7 +574,9 @@ int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_
     if (rc) return rc;
     if (cta < 0 || cta >= pl.P) return fail(WN_ERR_INVALID, "cta out of range");
     if (packed_floats < pl.cta_w_floats) return fail(WN_ERR_INVALID, "packed buffer too small");
-    pack_cta(pl, *w, cta, packed);
+    Folded fo;
+    fold_layers(pl, *w, fo);
+    pack_cta(pl, *w, fo, cta, packed);
     if (packed_floats >= pl.cta_w_floats + pl.cta_cw_floats) pack_cw_cta(pl, *w, cta, packed + pl.cta_w_floats);
     return WN_OK;
 }
@@ -540,6 +626,7 @@ int32_t wn_destroy(void* handle) {
     cudaFree(h->d_wpack); cudaFree(h->d_cwpack); cudaFree(h->d_wg); cudaFree(h->d_first_w); cudaFree(h->d_first_b);
     cudaFree(h->d_ringtab); cudaFree(h->d_err); cudaFree(h->d_xbuf); cudaFree(h->d_ring); cudaFree(h->d_gbias);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_prof);
     delete h;
     return WN_OK;
 }
@@ -560,7 +647,11 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
         return WN_OK;
     };
     std::vector<float> img((size_t)pl.P * pl.cta_w_floats);
-    for (int p = 0; p < pl.P; ++p) pack_cta(pl, *w, p, img.data() + (size_t)p * pl.cta_w_floats);
+    {
+        Folded fo;
+        fold_layers(pl, *w, fo);
+        for (int p = 0; p < pl.P; ++p) pack_cta(pl, *w, fo, p, img.data() + (size_t)p * pl.cta_w_floats);
+    }
     if ((rc = upload(&h->d_wpack, img))) return rc;
     std::vector<float> cw((size_t)pl.P * pl.cta_cw_floats);
     for (int p = 0; p < pl.P; ++p) pack_cw_cta(pl, *w, p, cw.data() + (size_t)p * pl.cta_cw_floats);
@@ -597,7 +688,7 @@ static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
     const wn_config& c = h->cfg;
     if (!a) return fail(WN_ERR_INVALID, "null args");
     if (a->B < 1 || a->T < 1) return fail(WN_ERR_INVALID, "B and T must be >= 1");
-    if ((long long)a->T * (2LL * c.layers + 3) >= 0xFFFFFFF0LL) return fail(WN_ERR_INVALID, "T too large for 32-bit tags");
+    if ((long long)a->T * (c.layers + 3LL) >= 0xFFFFFFF0LL) return fail(WN_ERR_INVALID, "T too large for 32-bit tags");
     if (c.cin_channels > 0 && !a->c) return fail(WN_ERR_INVALID, "c is required (cin_channels > 0), cf. train.py:82-87");
     if (c.cin_channels == 0 && a->c) return fail(WN_ERR_INVALID, "c given but the model has no local conditioning");
     if (c.gin_channels == 0 && a->g) return fail(WN_ERR_INVALID, "g given but the model has no global conditioning");
@@ -651,6 +742,17 @@ int32_t wn_sync(void* handle) {
     h->pending = false;
     int err[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpy(err, h->d_err, sizeof(err), cudaMemcpyDeviceToHost));
+    if (h->d_prof && env_int("WN_PROF", 0)) {
+        std::vector<long long> pc(h->prof_bytes / sizeof(long long));
+        CUDA_TRY(cudaMemcpy(pc.data(), h->d_prof, h->prof_bytes, cudaMemcpyDeviceToHost));
+        const char* names[8] = {"poll", "gemv_crit", "barrier", "finalize+publish", "deferred", "head+sample", "weights_wait", "x0+noise"};
+        const int P = (int)(pc.size() / 8);
+        for (int i = 0; i < 8; ++i) {
+            long long mn = pc[i], mx = pc[i], sum = 0;
+            for (int p = 0; p < P; ++p) { mn = std::min(mn, pc[p * 8 + i]); mx = std::max(mx, pc[p * 8 + i]); sum += pc[p * 8 + i]; }
+            fprintf(stderr, "WN_PROF %-18s mean %12.0f  min %12lld  max %12lld cycles\n", names[i], (double)sum / P, mn, mx);
+        }
+    }
     if (err[0] != 0) {
         cudaMemset(h->d_err, 0, sizeof(err));
         char buf[160];

@@ -4,19 +4,25 @@
 // T-step loop, including the sampler, runs on the device.  P thread blocks (one per SM,
 // cooperative launch) each own a fixed slice of the output rows of every matrix (wn_plan.h).
 //
-// Per generated sample, per layer l (modules.py:112-163, conv.py:17-46), a block does
-//   stage A: wait for x_l (R floats, broadcast through L2) -> its rows of the CURRENT tap of the
-//            dilated conv (+ bias + conditioning + the queued products of the older taps)
-//            -> tanh*sigmoid -> publish its slice of y_l.
-//            Deferred (off the critical path, done while y_l travels): the OLDER taps' products
-//            W[:, :, k<kw-1] . x_l(t), queued for steps t+d, t+2d (this replaces the reference's
-//            input shift register, conv.py:32-44, by a queue of OUTPUT partials that is private
-//            to the block and (kw-1)*d*rows long instead of (kw-1)*d*R).
-//   stage B: wait for y_l (G/2 floats) -> its rows of conv1x1_out -> residual, *sqrt(.5)
-//            -> publish its slice of x_{l+1}.  Deferred: its rows of conv1x1_skip, accumulated
-//            in layer order like wavenet.py:312.
-// then the head (wavenet.py:313-319) in two more stages and the sampler (mixture.py), which every
-// block evaluates redundantly from the same noise so no further broadcast is needed.
+// Per generated sample the blocks run L+3 "stages", each ending in ONE broadcast:
+//   stage 0      : x_0 (first 1x1 conv of the fed-back sample, computed by every block) ->
+//                  its rows of the current tap of layer 0 -> tanh*sigmoid -> publish y_0
+//   stage s<L    : wait for (y_{s-1}, x_{s-1}); then for layer s (modules.py:112-163)
+//                    z_s = M_{s-1} y_{s-1} + V_s x_{s-1} + bias + conditioning + queued older taps
+//                  where V_s = sqrt(.5) W_s[:,:,kw-1] and M_{s-1} = V_s Wo_{s-1} were folded on the host
+//                  (conv1x1_out of the previous layer rides inside the current tap, so the reference's
+//                  two dependent GEMVs per layer need one broadcast instead of two), and
+//                    x_s = (Wo_{s-1} y_{s-1} + bo + x_{s-1}) sqrt(.5)        (its rows; the residual stream)
+//                  -> publish (y_s, x_s) together.
+//                  Deferred, off the critical path while the broadcast travels: the OLDER taps'
+//                  products W_{s-1}[:,:,k<kw-1] . x_{s-1}(t), queued for steps t+d, t+2d (this replaces
+//                  the reference's input shift register, conv.py:32-44, by a queue of OUTPUT partials
+//                  private to the block), and its rows of conv1x1_skip_{s-1}, accumulated in layer
+//                  order like wavenet.py:312.
+//   stage L      : skip rows of the last layer -> total skip * sqrt(1/L) -> ReLU -> publish
+//   head 1, 2    : wavenet.py:315-319, one broadcast each
+// then the sampler (mixture.py), which every block evaluates redundantly from the same noise so
+// no further broadcast is needed.
 //
 // Exchange protocol: every value travels as an 8-byte (value, tag) pair (tag = step*NE+id+1),
 // written with one 8-byte store and polled with 8/16-byte loads, so data and "ready" flag are
@@ -62,6 +68,7 @@ struct WnPtrs {
     int noise_kind;
     unsigned long long seed;
     long long timeout_cycles;
+    long long* prof;           // optional [P][8] cycle counters (scripts/sweep.py --prof)
 };
 
 #define WN_FLAG_SOFTMAX_ 1u
@@ -212,7 +219,7 @@ __device__ __noinline__ bool wn_check_abort(volatile int* s_abort, int* err, lon
 }
 
 // ------------------------------------------------------------------------------------------
-template <int BT>
+template <int BT, int ER, int EG>
 struct Engine {
     const WnPlan& pl;
     const WnPtrs& pp;
@@ -274,38 +281,58 @@ struct Engine {
         return true;
     }
 
-    // ---- wait for a broadcast vector: thread owns elements k = tid + j*WN_NT
+    // ---- wait for a broadcast vector: thread owns elements k = tid + j*WN_NT.
+    // load_vec issues the loads of one attempt and returns the OR of the tag mismatches.
     template <int E>
-    __device__ __forceinline__ void poll_vec(const uint2* __restrict__ src, int K, uint32_t tag,
-                                             float (&x)[WN_MAXE][BT]) {
+    __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int K, uint32_t tag,
+                                                 float (&x)[E][BT]) {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = tid + j * WN_NT;
+            if (k < K) {
+                const uint2* s = src + (size_t)k * BT;
+                if constexpr (BT == 1) {
+                    const uint2 v = ld_pair(s);
+                    x[j][0] = __uint_as_float(v.x);
+                    bad |= v.y ^ tag;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BT; b += 2) {
+                        const uint4 v = ld_pair2(s + b);
+                        x[j][b] = __uint_as_float(v.x);
+                        bad |= v.y ^ tag;
+                        x[j][b + 1] = __uint_as_float(v.z);
+                        bad |= v.w ^ tag;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+            }
+        }
+        return bad;
+    }
+    template <int E>
+    __device__ __forceinline__ void poll_vec(const uint2* __restrict__ src, int K, uint32_t tag, float (&x)[E][BT]) {
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (load_vec<E>(src, K, tag, x) != 0) {
+            if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
+                dead = true;
+                return;
+            }
+        }
+    }
+    // two vectors of the same exchange (y then x): all loads of an attempt are in flight together
+    template <int EA, int EB>
+    __device__ __forceinline__ void poll_vec2(const uint2* __restrict__ srca, int KA, float (&a)[EA][BT],
+                                              const uint2* __restrict__ srcb, int KB, float (&b)[EB][BT],
+                                              uint32_t tag) {
         uint32_t spins = 0;
         long long t0 = 0;
         while (true) {
-            uint32_t bad = 0;
-#pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const int k = tid + j * WN_NT;
-                if (k < K) {
-                    const uint2* s = src + (size_t)k * BT;
-                    if constexpr (BT == 1) {
-                        const uint2 v = ld_pair(s);
-                        x[j][0] = __uint_as_float(v.x);
-                        bad |= v.y ^ tag;
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < BT; b += 2) {
-                            const uint4 v = ld_pair2(s + b);
-                            x[j][b] = __uint_as_float(v.x);
-                            bad |= v.y ^ tag;
-                            x[j][b + 1] = __uint_as_float(v.z);
-                            bad |= v.w ^ tag;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
-                }
-            }
+            const uint32_t bad = load_vec<EA>(srca, KA, tag, a) | load_vec<EB>(srcb, KB, tag, b);
             if (bad == 0) return;
             if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                 dead = true;
@@ -314,7 +341,7 @@ struct Engine {
         }
     }
     template <int E>
-    __device__ __forceinline__ void stash(float* dst, int K, const float (&x)[WN_MAXE][BT]) {
+    __device__ __forceinline__ void stash(float* dst, int K, const float (&x)[E][BT]) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int k = tid + j * WN_NT;
@@ -325,33 +352,41 @@ struct Engine {
         }
     }
 
-    // ---- rows x vector for NQ row quads; partial sums of warp w land in red[v*NWARP + w]
+    // ---- one row quad (4 rows x K) times the thread's slice of the input vector, accumulated
     template <int E>
-    __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K,
-                                         const float (&x)[WN_MAXE][BT], float* __restrict__ red) {
-        constexpr int NV = 4 * BT;
-        constexpr int M = ilog2c(NV);
-        for (int q = 0; q < NQ; ++q) {
-            float acc[NV];
+    __device__ __forceinline__ void quad_fma(const float* __restrict__ wq /* [K][4] */, int K,
+                                             const float (&x)[E][BT], float (&acc)[4 * BT]) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+        for (int j = 0; j < E; ++j) {
+            const int k = tid + j * WN_NT;
+            if (k < K) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wq + (size_t)k * 4);
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const int k = tid + j * WN_NT;
-                if (k < K) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w + ((size_t)q * K + k) * 4);
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) {
-                        acc[0 * BT + b] = fmaf(w4.x, x[j][b], acc[0 * BT + b]);
-                        acc[1 * BT + b] = fmaf(w4.y, x[j][b], acc[1 * BT + b]);
-                        acc[2 * BT + b] = fmaf(w4.z, x[j][b], acc[2 * BT + b]);
-                        acc[3 * BT + b] = fmaf(w4.w, x[j][b], acc[3 * BT + b]);
-                    }
+                for (int b = 0; b < BT; ++b) {
+                    acc[0 * BT + b] = fmaf(w4.x, x[j][b], acc[0 * BT + b]);
+                    acc[1 * BT + b] = fmaf(w4.y, x[j][b], acc[1 * BT + b]);
+                    acc[2 * BT + b] = fmaf(w4.z, x[j][b], acc[2 * BT + b]);
+                    acc[3 * BT + b] = fmaf(w4.w, x[j][b], acc[3 * BT + b]);
                 }
             }
-            reduce_scatter<NV>(acc, lane);
-            if ((lane & ((32 >> M) - 1)) == 0)
-                red[(q * NV + (lane >> (5 - M))) * WN_NWARP + warp] = acc[0];
+        }
+    }
+    // warp-reduce the 4*BT partial sums of quad `q`; warp w's result lands in red[v*NWARP + w]
+    __device__ __forceinline__ void quad_reduce(float (&acc)[4 * BT], int q, float* __restrict__ red) {
+        constexpr int NV = 4 * BT;
+        constexpr int M = ilog2c(NV);
+        reduce_scatter<NV>(acc, lane);
+        if ((lane & ((32 >> M) - 1)) == 0) red[(q * NV + (lane >> (5 - M))) * WN_NWARP + warp] = acc[0];
+    }
+    template <int E>
+    __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K, const float (&x)[E][BT],
+                                         float* __restrict__ red, int q0 = 0) {
+        for (int q = 0; q < NQ; ++q) {
+            float acc[4 * BT];
+#pragma unroll
+            for (int v = 0; v < 4 * BT; ++v) acc[v] = 0.f;
+            quad_fma<E>(w + (size_t)q * K * 4, K, x, acc);
+            quad_reduce(acc, q0 + q, red);
         }
     }
     __device__ __forceinline__ float red_sum(const float* red, int rowidx, int b) const {
@@ -367,17 +402,13 @@ struct Engine {
 
     // ---- weight slots
     __device__ __forceinline__ const float* acquire_blob(int t, int i) {
-        int slot;
-        uint32_t par;
         if (i < pl.nres) {
-            slot = i;
-            par = 0;
-        } else {
-            const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
-            slot = pl.nres + (int)(js % (uint32_t)pl.nring);
-            par = (js / (uint32_t)pl.nring) & 1u;
+            if (t == 0 && !wait_bar(&bar_full[i], 0, 0x80000000u | (uint32_t)i)) dead = true;
+            return slots + (size_t)i * pl.slot_floats;
         }
-        if (!wait_bar(&bar_full[slot], par, 0x80000000u | (uint32_t)i)) dead = true;
+        const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
+        const int slot = pl.nres + (int)(js % (uint32_t)pl.nring);
+        if (!wait_bar(&bar_full[slot], (js / (uint32_t)pl.nring) & 1u, 0x80000000u | (uint32_t)i)) dead = true;
         return slots + (size_t)slot * pl.slot_floats;
     }
     __device__ __forceinline__ void release_blob(int t, int i) {
@@ -394,11 +425,10 @@ struct Engine {
     __device__ void tma_loop() {
         if (lane != 0) return;
         const float* base = pp.wpack + (size_t)p * pl.cta_w_floats;
-        const uint32_t lbytes = (uint32_t)pl.lb_floats * 4u, hbytes = (uint32_t)pl.hb_floats * 4u;
         for (int i = 0; i < pl.nres; ++i) {
-            const uint32_t bytes = (i < pl.L) ? lbytes : hbytes;
+            const uint32_t bytes = (uint32_t)wn_blob_floats(pl, i) * 4u;
             mbar_expect_tx(&bar_full[i], bytes);
-            bulk_g2s(slots + (size_t)i * pl.slot_floats, base + (size_t)i * pl.lb_floats, bytes, &bar_full[i]);
+            bulk_g2s(slots + (size_t)i * pl.slot_floats, base + wn_blob_off(pl, i), bytes, &bar_full[i]);
         }
         const int nstream = pl.nblobs - pl.nres;
         if (nstream <= 0) return;
@@ -409,10 +439,10 @@ struct Engine {
             if (u > 0) {
                 if (!wait_bar(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
             }
-            const uint32_t bytes = (i < pl.L) ? lbytes : hbytes;
+            const uint32_t bytes = (uint32_t)wn_blob_floats(pl, i) * 4u;
             uint64_t* fb = &bar_full[pl.nres + s];
             mbar_expect_tx(fb, bytes);
-            bulk_g2s(slots + (size_t)(pl.nres + s) * pl.slot_floats, base + (size_t)i * pl.lb_floats, bytes, fb);
+            bulk_g2s(slots + (size_t)(pl.nres + s) * pl.slot_floats, base + wn_blob_off(pl, i), bytes, fb);
             if (++i == pl.nblobs) i = pl.nres;
         }
     }
@@ -584,7 +614,9 @@ struct Engine {
                     if (writer && b < pp.B) pp.out_dense[((size_t)b * O + i) * T + t] = v;
                     s_dense[b * O + i] = v;
                 }
-                if (lane == 0) s_idx[b] = -1;
+                if (lane == 0)
+                    s_idx[b] = (t + 1 < pp.T_test && b < pp.B && pp.test_index)
+                                   ? pp.test_index[(size_t)b * pp.T_test + t + 1] : -1;
             }
             // teacher forcing with dense rows overrides the feedback
             if (t + 1 < pp.T_test && pp.test_dense != nullptr && b < pp.B) {
@@ -640,11 +672,10 @@ struct Engine {
     // ======================================================================================
     __device__ __forceinline__ static int efor(int K) { return K <= WN_NT ? 1 : (K <= 2 * WN_NT ? 2 : 4); }
 
-    template <int E>
-    __device__ __forceinline__ void make_x0(float (&x)[WN_MAXE][BT]) {
+    __device__ __forceinline__ void make_x0(float (&x)[ER][BT]) {
         const int R = pl.R, O = pl.O;
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
+        for (int j = 0; j < ER; ++j) {
             const int k = tid + j * WN_NT;
 #pragma unroll
             for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
@@ -670,14 +701,55 @@ struct Engine {
                 }
             }
         }
-        stash<E>(xs, R, x);
+        stash<ER>(xs, R, x);
     }
 
-#define WN_DISPATCH_E(EV, ...)                       \
-    switch (EV) {                                    \
-        case 1: { constexpr int E = 1; __VA_ARGS__; } break; \
-        case 2: { constexpr int E = 2; __VA_ARGS__; } break; \
-        default: { constexpr int E = 4; __VA_ARGS__; } break; \
+#define WN_DISPATCH_E(EV, ...)                                \
+    switch (EV) {                                             \
+        case 1: { constexpr int E = 1; __VA_ARGS__ } break;   \
+        case 2: { constexpr int E = 2; __VA_ARGS__ } break;   \
+        default: { constexpr int E = 4; __VA_ARGS__ } break;  \
+    }
+
+    // ---- finalizers (64-thread groups, see wn_plan.h) ------------------------------------
+    // everything of z_s that does not depend on this stage's broadcast, for gate pair `fr`
+    __device__ __forceinline__ void gate_pre(int t, int l, int fr, int fb, float& pre_a, float& pre_b) {
+        const int RA4 = pl.RA4, kw = pl.kw, ra = 2 * fr, rb = 2 * fr + 1;
+        pre_a = sb[((size_t)l * RA4 + ra) * BT + fb];
+        pre_b = sb[((size_t)l * RA4 + rb) * BT + fb];
+        if (pl.C > 0) {
+            const float* cd = cond + ((size_t)(t & 1) * pl.L + l) * RA4 * BT;
+            pre_a += cd[ra * BT + fb];
+            pre_b += cd[rb * BT + fb];
+        }
+        for (int k = 0; k < kw - 1; ++k) {
+            const int off = ringtab[(l * (kw - 1) + k) * 2], D = ringtab[(l * (kw - 1) + k) * 2 + 1];
+            const volatile float* rp = ring + ((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT;
+            pre_a += rp[ra * BT + fb];
+            pre_b += rp[rb * BT + fb];
+        }
+    }
+    // gate outputs of layer l -> y part of exchange l
+    __device__ __forceinline__ void finalize_gates(int t, int l, int y0, int ny, uint32_t tag, float pre_a, float pre_b) {
+        const int n = ny * BT;
+        for (int f = tid - WN_FIN_Y; f < n; f += WN_FIN_W) {
+            const int fr = f / BT, fb = f % BT;
+            if (f != tid - WN_FIN_Y) gate_pre(t, l, fr, fb, pre_a, pre_b);    // extra items: not pre-summed
+            const float a = red_sum(red1, 2 * fr, fb) + pre_a;
+            const float g = red_sum(red1, 2 * fr + 1, fb) + pre_b;
+            const float yv = tanhf(a) * (1.0f / (1.0f + expf(-g)));            // modules.py:154
+            publish(pl.ex_yx + l * (pl.G2 + pl.R), y0 + fr, fb, yv, tag);
+        }
+    }
+    // queued older-tap products of `layer` (partials in red2 buffer `buf`) -> history ring
+    __device__ __forceinline__ void finalize_ring(int t, int layer, const float* buf) {
+        const int kw = pl.kw, n = (kw - 1) * pl.RA * BT;
+        for (int f = tid - WN_FIN_RING; f < n; f += WN_FIN_W) {
+            const int dr = f / BT, db = f % BT, tap = dr / pl.RA, rr = dr % pl.RA;
+            const float v = red_sum(buf, dr, db);
+            const int off = ringtab[(layer * (kw - 1) + tap) * 2], D = ringtab[(layer * (kw - 1) + tap) * 2 + 1];
+            ring[((size_t)off + (uint32_t)t % (uint32_t)D) * pl.RA4 * BT + rr * BT + db] = v;
+        }
     }
 
     __device__ void compute_loop() {
@@ -689,18 +761,23 @@ struct Engine {
         wn_part(S, P, p, s0, ns);
         wn_part(S, P, p, a0, na);
         wn_part(O, P, p, b0, nb);
-        const int ER = efor(R), EG = efor(G2), ES = efor(S), EO = efor(O);
+        const int ES = efor(S), EO = efor(O);
         const uint2* xin = pp.xbuf + (size_t)(p % pl.ncopy) * pl.copy_stride_pairs;
-        const uint32_t NEID = 2u * L + 3u;
-        const int RA4 = pl.RA4;
-        const int fr = tid / BT, fb = tid % BT;              // finalizer role: (row, utterance)
-        const int dt = tid - WN_NT / 2;                       // deferred-finalizer index
-        const int dr = dt >= 0 ? dt / BT : 0, db = dt >= 0 ? dt % BT : 0;
+        const uint32_t NEID = (uint32_t)L + 3u;
+        const int YX = G2 + R;
         const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
-        float* red2A = red2;                                  // older-tap products of stage A
-        float* red2B = red2 + (size_t)pl.NQ_D * 4 * BT * WN_NWARP;   // skip rows of stage B
-        float x[WN_MAXE][BT];
-        float skipb_prev = 0.f;   // skip bias of the previous layer for this thread's deferred row
+        const int red2B_off = pl.NQ_D * 4 * BT * WN_NWARP;    // skip partials follow the tap partials
+        float* skb0 = skipacc + pl.NSm * BT;                  // skip bias of the layer whose rows are pending,
+        const int skbN = 4 * pl.NQ_BS;                        // double-buffered by stage parity
+        const bool finY = (tid >= WN_FIN_Y && tid < WN_FIN_Y + WN_FIN_W);
+        const bool finX = (tid >= WN_FIN_X && tid < WN_FIN_X + WN_FIN_W);
+        const bool finR = (tid >= WN_FIN_RING && tid < WN_FIN_RING + WN_FIN_W);
+        const bool finS = (tid >= WN_FIN_SKIP && tid < WN_FIN_SKIP + WN_FIN_W);
+        const int f0r = (tid - WN_FIN_Y) / BT, f0b = (tid - WN_FIN_Y) % BT;   // first gate item of a Y-group thread
+        float xr[ER][BT], yr[EG][BT];
+        const bool prof = (pp.prof != nullptr) && tid == 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+#define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
 
         // feedback for step 0 (wavenet.py:281-301)
         if (tid < BT) {
@@ -729,118 +806,164 @@ struct Engine {
 
         for (int t = 0; t < T; ++t) {
             const uint32_t tagbase = (uint32_t)t * NEID + 1u;
+            if (prof) tc = clock64();
             if (pl.C > 0) {
                 if (!wait_bar(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
             }
-            WN_DISPATCH_E(ER, make_x0<E>(x));
+            make_x0(xr);
             if (warp < BT) fetch_noise(t, warp);
-
-            for (int l = 0; l < L; ++l) {
-                const float* W = acquire_blob(t, l);
-                const bool last = (l == L - 1);
-                // ------------------------------------------------------------ stage A
-                // everything that does not depend on x_l(t) is summed before the wait
+            WN_TICK(7);
+            // ------------------------------------------------------------ stage 0: layer 0 from x_0
+            {
+                const float* W = acquire_blob(t, 0);
+                WN_TICK(6);
                 float pre_a = 0.f, pre_b = 0.f;
-                const bool finA = (tid < pl.NYm * BT) && (fr < ny);
-                if (finA) {
-                    const int ra = 2 * fr, rb = 2 * fr + 1;
-                    pre_a = sb[((size_t)l * RA4 + ra) * BT + fb];
-                    pre_b = sb[((size_t)l * RA4 + rb) * BT + fb];
-                    if (pl.C > 0) {
-                        const float* cd = cond + ((size_t)(t & 1) * L + l) * RA4 * BT;
-                        pre_a += cd[ra * BT + fb];
-                        pre_b += cd[rb * BT + fb];
-                    }
-                    for (int k = 0; k < kw - 1; ++k) {
-                        const int off = ringtab[(l * (kw - 1) + k) * 2], D = ringtab[(l * (kw - 1) + k) * 2 + 1];
-                        const volatile float* rp = ring + ((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT;
-                        pre_a += rp[ra * BT + fb];
-                        pre_b += rp[rb * BT + fb];
-                    }
-                }
-                if (l > 0) {
-                    const uint2* src = xin + (size_t)(pl.ex_x + l * R) * BT;
-                    WN_DISPATCH_E(ER, poll_vec<E>(src, R, tagbase + wn_eid_x(l), x); stash<E>(xs, R, x));
-                }
-                WN_DISPATCH_E(ER, gemv<E>(W + pl.lb_Acrit, pl.NQ_A, R, x, red1));
-                if (bar_or(dead)) return;                                            // S1
-                if (finA) {
-                    const float a = red_sum(red1, 2 * fr, fb) + pre_a;
-                    const float g = red_sum(red1, 2 * fr + 1, fb) + pre_b;
-                    const float yv = tanhf(a) * (1.0f / (1.0f + expf(-g)));            // modules.py:154
-                    publish(pl.ex_y + l * G2, y0 + fr, fb, yv, tagbase + wn_eid_y(l));
-                }
-                if (l > 0 && dt >= 0 && dt < pl.NSm * BT && dr < ns) {
-                    // deferred from layer l-1: its skip rows, accumulated in layer order (wavenet.py:312)
-                    const float h = red_sum(red2B, dr, db) + skipb_prev;
-                    skipacc[dr * BT + db] = (l == 1) ? h : skipacc[dr * BT + db] + h;
-                }
-                if (last && pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // cond[t&1] consumed
-                if (kw > 1) { WN_DISPATCH_E(ER, gemv<E>(W + pl.lb_Adef, pl.NQ_D, R, x, red2A)); }
-                // ------------------------------------------------------------ stage B
-                {
-                    const uint2* src = xin + (size_t)(pl.ex_y + l * G2) * BT;
-                    WN_DISPATCH_E(EG, poll_vec<E>(src, G2, tagbase + wn_eid_y(l), x));
-                }
-                if (!last) { WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bo, pl.NQ_BO, G2, x, red1)); }
-                else { WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bs, pl.NQ_BS, G2, x, red1)); }
-                if (bar_or(dead)) return;                                            // S2
-                if (!last) {
-                    if (tid < pl.NXm * BT && fr < nx) {
-                        // modules.py:160-162  (conv1x1_out(y) + residual) * sqrt(0.5)
-                        const float o = red_sum(red1, fr, fb) + W[pl.lb_outb + fr];
-                        const float xn = (o + xs[(x0r + fr) * BT + fb]) * RSQRT2;
-                        publish(pl.ex_x + (l + 1) * R, x0r + fr, fb, xn, tagbase + wn_eid_x(l + 1));
-                    }
-                } else {
-                    if (tid < pl.NSm * BT && fr < ns) {
-                        // last layer: its residual output is never used (wavenet.py:310-313); finish
-                        // the skip sum, scale by sqrt(1/L) and apply the first ReLU of the head
-                        const float h = red_sum(red1, fr, fb) + W[pl.lb_skipb + fr];
-                        const float tot = (L == 1) ? h : skipacc[fr * BT + fb] + h;
-                        const float sk = fmaxf(tot * pl.skip_scale, 0.f);
-                        publish(pl.ex_sk, s0 + fr, fb, sk, tagbase + wn_eid_sk(pl));
-                    }
-                }
-                if (kw > 1 && dt >= 0 && dt < (kw - 1) * pl.RA * BT) {
-                    // deferred from stage A: queue the older taps' products (conv.py:32-44 restated)
-                    const int tap = dr / pl.RA, rr = dr % pl.RA;
-                    const float v = red_sum(red2A, dr, db);
-                    const int off = ringtab[(l * (kw - 1) + tap) * 2], D = ringtab[(l * (kw - 1) + tap) * 2 + 1];
-                    ring[((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT + rr * BT + db] = v;
-                }
-                if (!last) {
-                    if (dt >= 0 && dt < pl.NSm * BT) skipb_prev = W[pl.lb_skipb + dr];
-                    WN_DISPATCH_E(EG, gemv<E>(W + pl.lb_Bs, pl.NQ_BS, G2, x, red2B));
-                }
-                release_blob(t, l);
+                if (finY && f0r < ny) gate_pre(t, 0, f0r, f0b, pre_a, pre_b);
+                gemv<ER>(W + pl.fb_Zx, pl.NQ_A, R, xr, red1);
+                WN_TICK(1);
+                if (bar_or(dead)) return;
+                WN_TICK(2);
+                if (finY) finalize_gates(t, 0, y0, ny, tagbase + wn_eid_yx(0), pre_a, pre_b);
+                release_blob(t, 0);
+                WN_TICK(3);
             }
-            // ---------------------------------------------------------------- head (wavenet.py:313-319)
+            // ------------------------------------------------------------ stages 1..L-1
+            for (int s = 1; s < L; ++s) {
+                const float* W = acquire_blob(t, s);
+                WN_TICK(6);
+                float pre_a = 0.f, pre_b = 0.f;
+                if (finY && f0r < ny) gate_pre(t, s, f0r, f0b, pre_a, pre_b);
+                {
+                    const uint2* src = xin + (size_t)(pl.ex_yx + (s - 1) * YX) * BT;
+                    const uint32_t tag = tagbase + wn_eid_yx(s - 1);
+                    if (s >= 2) {
+                        poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
+                        stash<ER>(xs, R, xr);
+                    } else {
+                        poll_vec<EG>(src, G2, tag, yr);       // x_0 is already in registers
+                    }
+                }
+                WN_TICK(0);
+                // critical: gate pre-activations of layer s and the residual rows x_s
+                for (int q = 0; q < pl.NQ_A; ++q) {
+                    float acc[4 * BT];
+#pragma unroll
+                    for (int v = 0; v < 4 * BT; ++v) acc[v] = 0.f;
+                    quad_fma<EG>(W + pl.lb_Zy + (size_t)q * G2 * 4, G2, yr, acc);
+                    quad_fma<ER>(W + pl.lb_Zx + (size_t)q * R * 4, R, xr, acc);
+                    quad_reduce(acc, q, red1);
+                }
+                gemv<EG>(W + pl.lb_Xo, pl.NQ_BO, G2, yr, red1, pl.NQ_A);
+                WN_TICK(1);
+                if (bar_or(dead)) return;
+                WN_TICK(2);
+                const uint32_t tag = tagbase + wn_eid_yx(s);
+                if (finY) finalize_gates(t, s, y0, ny, tag, pre_a, pre_b);
+                if (finX) {
+                    // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
+                    for (int f = tid - WN_FIN_X; f < nx * BT; f += WN_FIN_W) {
+                        const int fr = f / BT, fb = f % BT;
+                        const float o = red_sum(red1, pl.NQ_A * 4 + fr, fb) + W[pl.lb_xb + fr];
+                        const float xn = (o + xs[(x0r + fr) * BT + fb]) * RSQRT2;
+                        publish(pl.ex_yx + s * YX + G2, x0r + fr, fb, xn, tag);
+                    }
+                }
+                const float* prev = red2 + (size_t)((s - 1) & 1) * pl.red2_floats;
+                if (finR && s >= 2 && kw > 1) finalize_ring(t, s - 2, prev);
+                if (finS) {
+                    if (s >= 2) {
+                        // skip rows of layer s-2, accumulated in layer order (wavenet.py:312)
+                        for (int f = tid - WN_FIN_SKIP; f < ns * BT; f += WN_FIN_W) {
+                            const int fr = f / BT, fb = f % BT;
+                            const float h = red_sum(prev + red2B_off, fr, fb) + skb0[((s - 1) & 1) * skbN + fr];
+                            skipacc[f] = (s == 2) ? h : skipacc[f] + h;
+                        }
+                    }
+                    for (int r = tid - WN_FIN_SKIP; r < ns; r += WN_FIN_W)
+                        skb0[(s & 1) * skbN + r] = W[pl.lb_sb + r];                  // bias of layer s-1
+                }
+                WN_TICK(3);
+                // deferred: older taps and skip rows of layer s-1
+                float* cur = red2 + (size_t)(s & 1) * pl.red2_floats;
+                if (kw > 1) gemv<ER>(W + pl.lb_Td, pl.NQ_D, R, xr, cur);
+                gemv<EG>(W + pl.lb_Sk, pl.NQ_BS, G2, yr, cur + red2B_off);
+                release_blob(t, s);
+                WN_TICK(4);
+            }
+            // ------------------------------------------------------------ stage L: skip of the last layer
             const float* H = acquire_blob(t, L);
+            WN_TICK(6);
+            {
+                const uint2* src = xin + (size_t)(pl.ex_yx + (L - 1) * YX) * BT;
+                const uint32_t tag = tagbase + wn_eid_yx(L - 1);
+                if (L >= 2) {
+                    poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
+                } else {
+                    poll_vec<EG>(src, G2, tag, yr);
+                }
+            }
+            WN_TICK(0);
+            gemv<EG>(H + pl.tb_Sk, pl.NQ_BS, G2, yr, red1);
+            WN_TICK(1);
+            if (bar_or(dead)) return;
+            WN_TICK(2);
+            if (pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // every gate of step t has read cond[t&1]
+            {
+                const float* prev = red2 + (size_t)((L - 1) & 1) * pl.red2_floats;
+                if (finS) {
+                    // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
+                    for (int f = tid - WN_FIN_SKIP; f < ns * BT; f += WN_FIN_W) {
+                        const int fr = f / BT, fb = f % BT;
+                        float tot = red_sum(red1, fr, fb) + H[pl.tb_sb + fr];
+                        if (L >= 2) {
+                            const float pend = red_sum(prev + red2B_off, fr, fb) + skb0[((L - 1) & 1) * skbN + fr];
+                            tot = ((L >= 3) ? skipacc[f] + pend : pend) + tot;
+                        }
+                        publish(pl.ex_sk, s0 + fr, fb, fmaxf(tot * pl.skip_scale, 0.f), tagbase + wn_eid_sk(pl));
+                    }
+                }
+                if (finR && L >= 2 && kw > 1) finalize_ring(t, L - 2, prev);
+            }
+            WN_TICK(3);
+            float* tailbuf = red2 + (size_t)(L & 1) * pl.red2_floats;
+            if (kw > 1) gemv<ER>(H + pl.tb_Td, pl.NQ_D, R, xr, tailbuf);      // older taps of layer L-1
+            WN_TICK(4);
+            // ---------------------------------------------------------------- head (wavenet.py:315-319)
             if (na > 0) {
                 const uint2* src = xin + (size_t)pl.ex_sk * BT;
-                WN_DISPATCH_E(ES, poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), x);
-                              gemv<E>(H + pl.hb_Ha, pl.NQ_HA, S, x, red1));
+                WN_DISPATCH_E(ES, { float h[E][BT];
+                                    poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), h);
+                                    gemv<E>(H + pl.tb_Ha, pl.NQ_HA, S, h, red1); });
             }
             if (bar_or(dead)) return;                                                // S3
-            if (tid < pl.NAm * BT && fr < na) {
-                const float h1 = fmaxf(red_sum(red1, fr, fb) + H[pl.hb_Hab + fr], 0.f);
-                publish(pl.ex_h1, a0 + fr, fb, h1, tagbase + wn_eid_h1(pl));
+            if (finY) {
+                for (int f = tid - WN_FIN_Y; f < na * BT; f += WN_FIN_W) {
+                    const int fr = f / BT, fb = f % BT;
+                    const float h1 = fmaxf(red_sum(red1, fr, fb) + H[pl.tb_Hab + fr], 0.f);
+                    publish(pl.ex_h1, a0 + fr, fb, h1, tagbase + wn_eid_h1(pl));
+                }
             }
+            if (finR && kw > 1) finalize_ring(t, L - 1, tailbuf);
             if (nb > 0) {
                 const uint2* src = xin + (size_t)pl.ex_h1 * BT;
-                WN_DISPATCH_E(ES, poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), x);
-                              gemv<E>(H + pl.hb_Hb, pl.NQ_HB, S, x, red1));
+                WN_DISPATCH_E(ES, { float h[E][BT];
+                                    poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), h);
+                                    gemv<E>(H + pl.tb_Hb, pl.NQ_HB, S, h, red1); });
             }
             if (bar_or(dead)) return;                                                // S4
-            if (tid < pl.NBm * BT && fr < nb) {
-                const float h2 = red_sum(red1, fr, fb) + H[pl.hb_Hbb + fr];
-                publish(pl.ex_h2, b0 + fr, fb, h2, tagbase + wn_eid_h2(pl));
+            if (finY) {
+                for (int f = tid - WN_FIN_Y; f < nb * BT; f += WN_FIN_W) {
+                    const int fr = f / BT, fb = f % BT;
+                    const float h2 = red_sum(red1, fr, fb) + H[pl.tb_Hbb + fr];
+                    publish(pl.ex_h2, b0 + fr, fb, h2, tagbase + wn_eid_h2(pl));
+                }
             }
             release_blob(t, L);
             {
                 const uint2* src = xin + (size_t)pl.ex_h2 * BT;
-                WN_DISPATCH_E(EO, poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), x); stash<E>(hs, O, x));
+                WN_DISPATCH_E(EO, { float h[E][BT];
+                                    poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), h);
+                                    stash<E>(hs, O, h); });
             }
             if (bar_or(dead)) return;                                                // S5
             if (p == 0 && pp.params_out != nullptr) {
@@ -853,19 +976,23 @@ struct Engine {
             }
             if (warp < BT) sample_utt(t, warp);
             if (bar_or(false)) return;                                               // S6
+            WN_TICK(5);
         }
+        if (prof) {
+            for (int i = 0; i < 8; ++i) pp.prof[(size_t)p * 8 + i] = pc[i];
+        }
+#undef WN_TICK
     }
 };
-
 
 // ------------------------------------------------------------------------------------------
 // kernel entry
 // ------------------------------------------------------------------------------------------
-template <int BT>
+template <int BT, int ER, int EG>
 __global__ void __launch_bounds__(WN_NTHREADS, 1)
 wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ WnPtrs pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Engine<BT> eng(pl, pp, smem_raw);
+    Engine<BT, ER, EG> eng(pl, pp, smem_raw);
     const int tid = threadIdx.x, p = blockIdx.x;
     const int nslots = pl.nres + pl.nring;
     if (tid == 0) {
@@ -883,7 +1010,7 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         const size_t n = (size_t)pl.ring_pos_total * pl.RA4 * BT;
         for (size_t i = tid; i < n; i += WN_NTHREADS) eng.ring[i] = 0.f;
     }
-    for (int i = tid; i < pl.NSm * BT; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
+    for (int i = tid; i < pl.NSm * BT + 8 * pl.NQ_BS; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
     for (int i = tid; i < pl.L * (pl.kw - 1) * 2; i += WN_NTHREADS) eng.ringtab[i] = pp.ringtab[i];
     for (int k = tid; k < pl.R; k += WN_NTHREADS) {
         eng.first[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
@@ -900,7 +1027,7 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
             const int b = i % BT, rr = (i / BT) % pl.RA4, l = i / (BT * pl.RA4);
             float v = 0.f;
             if (rr < pl.RA && (rr >> 1) < ny) {
-                v = blob0[(size_t)l * pl.lb_floats + pl.lb_convb + rr];
+                v = blob0[wn_blob_off(pl, l) + (l == 0 ? pl.fb_zb : pl.lb_zb) + rr];
                 if (pp.gbias != nullptr && b < pp.B) {
                     const int grow = (rr & 1) ? pl.G2 + y0 + (rr >> 1) : y0 + (rr >> 1);
                     v += pp.gbias[((size_t)b * pl.L + l) * pl.G + grow];

@@ -40,25 +40,34 @@ struct WnPlan {
     int RA;       // 2*NYm : rows of the dilated conv a block evaluates (a_j, b_j interleaved)
     // row quads per group ("quad-major" layout [quad][k][4 rows], one 16-byte smem load feeds 4 rows)
     int NQ_A, NQ_D, NQ_BO, NQ_BS, NQ_HA, NQ_HB;
-    // ---- layer blob, offsets in floats
-    int lb_Acrit;   // current tap  (k = kw-1): needed on the critical path
-    int lb_Adef;    // older taps   (k < kw-1): their products are queued for steps t+d, t+2d ...
-    int lb_convb;   // conv bias for the RA rows
-    int lb_Bo, lb_Bs, lb_outb, lb_skipb;
+    // ---- blobs (offsets in floats).  Stage s of a step evaluates layer s from (y_{s-1}, x_{s-1}):
+    //   z_s = M_{s-1} y_{s-1} + V_s x_{s-1} + ...   with V_s = sqrt(.5) W_s[:,:,kw-1],  M_{s-1} = V_s Wo_{s-1}
+    // so conv1x1_out of layer s-1 is folded into the current tap of layer s and one broadcast per
+    // layer (y_s and x_s together) is enough.
+    // first blob (stage 0): current tap of layer 0 + bias
+    int fb_Zx, fb_zb, fb_floats;
+    // layer blob (stage s = 1..L-1)
+    int lb_Zy;      // M_{s-1} rows          [NQ_A][G2][4]
+    int lb_Zx;      // V_s rows              [NQ_A][R][4]
+    int lb_Xo;      // conv1x1_out_{s-1} rows [NQ_BO][G2][4]  (the residual stream itself, published as x_s)
+    int lb_Td;      // older taps of layer s-1 [NQ_D][R][4]   (deferred: queued for steps t+d, t+2d ...)
+    int lb_Sk;      // conv1x1_skip_{s-1} rows [NQ_BS][G2][4] (deferred)
+    int lb_zb, lb_xb, lb_sb;   // biases: conv_b_s + V_s bo_{s-1} | bo_{s-1} | bs_{s-1}
     int lb_floats;
-    // ---- head blob
-    int hb_Ha, hb_Hab, hb_Hb, hb_Hbb, hb_floats;
-    int slot_floats;            // shared-memory slot size (>= both blobs)
-    long long cta_w_floats;     // packed floats per block = L*lb_floats + hb_floats
+    // tail blob (stage L + head): older taps and skip rows of layer L-1, then the two head matrices
+    int tb_Td, tb_Sk, tb_sb, tb_Ha, tb_Hab, tb_Hb, tb_Hbb, tb_floats;
+    int slot_floats;            // shared-memory slot size (>= every blob)
+    long long cta_w_floats;     // packed floats per block = fb + (L-1)*lb + tb
     int nblobs;                 // L + 1 per step
     int nres;                   // blobs [0,nres) stay resident in shared memory for the whole call
     int nring;                  // the others stream through nring slots every step
     // ---- conditioning weights (kept in L2, read by the conditioning warp): [L][NQ_A][C][4]
     long long cta_cw_floats;
-    // ---- exchange: element offsets (multiply by BT for pairs) of each vector inside one copy
-    int NE;                     // exchanges per step = 2L+2 (tags use 2L+3 ids)
+    // ---- exchange: element offsets (multiply by BT for pairs) of each vector inside one copy.
+    // exchange s (0..L-1) carries y_s (G2) then x_s (R); then skip (S), head hidden (S), head out (O)
+    int NE;                     // exchanges per step = L+3
     int ncopy;
-    int ex_x, ex_y, ex_sk, ex_h1, ex_h2, ex_elems;
+    int ex_yx, ex_sk, ex_h1, ex_h2, ex_elems;
     long long copy_stride_pairs;
     // ---- batch tile
     int BT;
@@ -69,6 +78,7 @@ struct WnPlan {
     // ---- shared memory map (byte offsets)
     int sm_bar, sm_misc, sm_ringtab, sm_xs, sm_red1, sm_red2, sm_sb, sm_cond, sm_skipacc, sm_hs,
         sm_noise, sm_in, sm_first, sm_ring, sm_slots, smem_bytes;
+    int red2_floats;            // one of the two deferred-partials buffers
     float skip_scale;           // sqrt(1/L), wavenet.py:313
 };
 
@@ -81,9 +91,21 @@ WN_HD void wn_part(int rows, int P, int p, int& base, int& cnt) {
 
 WN_HD int wn_ceil_div(int a, int b) { return (a + b - 1) / b; }
 WN_HD int wn_dilation(const WnPlan& pl, int l) { return 1 << (l % pl.per_stack); }
-// exchange ids within a step (tag = t*(2L+3) + id + 1)
-WN_HD int wn_eid_x(int l) { return 2 * l - 1; }      // input of layer l >= 1
-WN_HD int wn_eid_y(int l) { return 2 * l; }          // gated activation of layer l
-WN_HD int wn_eid_sk(const WnPlan& pl) { return 2 * pl.L; }
-WN_HD int wn_eid_h1(const WnPlan& pl) { return 2 * pl.L + 1; }
-WN_HD int wn_eid_h2(const WnPlan& pl) { return 2 * pl.L + 2; }
+// exchange ids within a step (tag = t*(L+3) + id + 1)
+WN_HD int wn_eid_yx(int s) { return s; }              // (y_s, x_s), s = 0..L-1
+WN_HD int wn_eid_sk(const WnPlan& pl) { return pl.L; }
+WN_HD int wn_eid_h1(const WnPlan& pl) { return pl.L + 1; }
+WN_HD int wn_eid_h2(const WnPlan& pl) { return pl.L + 2; }
+// float offset of blob i inside a block's packed image, and its size
+WN_HD long long wn_blob_off(const WnPlan& pl, int i) {
+    return i == 0 ? 0 : (long long)pl.fb_floats + (long long)(i - 1) * pl.lb_floats;
+}
+WN_HD int wn_blob_floats(const WnPlan& pl, int i) {
+    return i == 0 ? pl.fb_floats : (i < pl.L ? pl.lb_floats : pl.tb_floats);
+}
+// finalizer thread groups (64 threads each): gate outputs | residual rows | queued taps | skip rows
+#define WN_FIN_Y 0
+#define WN_FIN_X 64
+#define WN_FIN_RING 128
+#define WN_FIN_SKIP 192
+#define WN_FIN_W 64
