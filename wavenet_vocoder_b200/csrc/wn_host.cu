@@ -51,7 +51,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     if (c.kernel_size < 1 || c.kernel_size > 8) return fail(WN_ERR_INVALID, "kernel_size out of range [1,8]");
     if (c.residual_channels < 1 || c.skip_channels < 1 || c.out_channels < 1)
         return fail(WN_ERR_INVALID, "channel counts must be positive");
-    const int maxK = WN_MAXE * WN_NT;
+    const int maxK = WN_MAXE * 128;
     if (c.residual_channels > maxK || c.gate_channels / 2 > maxK || c.skip_channels > maxK || c.out_channels > maxK)
         return fail(WN_ERR_INVALID, "a stage vector exceeds 1024 entries (unsupported shape)");
     if (c.cin_channels < 0 || c.cin_channels > 32 * WN_MAX_CI)
@@ -145,8 +145,13 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     // ---- exchange map
     pl.NE = pl.L + 3;
     int nc = c.exchange_copies > 0 ? c.exchange_copies : env_int("WN_NCOPY", 0);
-    if (nc <= 0) nc = 1;
-    pl.ncopy = std::min(nc, P);
+    // every (row, utterance) item of a broadcast is finalised by one thread per replica inside a
+    // 64-thread group, so items * replicas <= 64
+    const int max_items = std::max(std::max(pl.NYm, pl.NXm), std::max(pl.NSm, std::max(pl.NAm, pl.NBm))) * BT;
+    if (max_items > 64) return fail(WN_ERR_INVALID, "too many rows per block for this batch tile (use more blocks)");
+    if (nc <= 0) nc = 8;
+    nc = std::min(nc, 64 / max_items);
+    pl.ncopy = std::max(1, std::min(nc, P));
     pl.ex_yx = 0;
     pl.ex_sk = pl.L * (pl.G2 + pl.R);
     pl.ex_h1 = pl.ex_sk + pl.S;
@@ -181,11 +186,12 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_misc = take(16, 16);
         pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
         pl.sm_ringtab = take((long long)ringtab.size() * 4 + 16, 16);
-        pl.sm_xs = take((long long)pl.R * BT * 4, 16);
+        pl.sm_xs = take(2LL * (pl.R + pl.G2) * BT * 4, 16);   // stash of (x, y), double buffered by stage parity
         const int nq1 = std::max(pl.NQ_A + pl.NQ_BO, std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
-        pl.sm_red1 = take((long long)nq1 * 4 * BT * WN_NWARP * 4, 16);
-        pl.red2_floats = (pl.NQ_D + pl.NQ_BS) * 4 * BT * WN_NWARP + 4;
-        pl.sm_red2 = take(2LL * pl.red2_floats * 4, 16);      // two buffers, alternating by stage
+        pl.red1_floats = nq1 * 4 * BT * 4 + 4;                // partial sums of the 4 warps of a group
+        pl.sm_red1 = take(2LL * pl.red1_floats * 4, 16);
+        pl.red2_floats = (pl.NQ_D + pl.NQ_BS) * 4 * BT * 4 + 4;
+        pl.sm_red2 = take(2LL * pl.red2_floats * 4, 16);      // two buffers each, alternating by stage
         pl.sm_sb = take((long long)pl.L * pl.RA4 * BT * 4, 16);
         pl.sm_cond = take(pl.C > 0 ? 2LL * pl.L * pl.RA4 * BT * 4 : 16, 16);
         pl.sm_skipacc = take((long long)(pl.NSm * BT + 8 * pl.NQ_BS) * 4 + 16, 16);   // running skip sum + 2 bias stashes
@@ -424,7 +430,7 @@ struct WnHandle {
     cudaStream_t last_stream = nullptr;
     bool pending = false;
     int64_t launches = 0;
-    bool attr_set[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+    bool attr_set[16] = {};
 };
 
 template <typename T>
@@ -509,7 +515,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
     pp.prof = nullptr;
     if (env_int("WN_PROF", 0)) {
-        const size_t pb = (size_t)pl.P * 8 * sizeof(long long);
+        const size_t pb = (size_t)pl.P * 16 * sizeof(long long);
         rc = ensure(&h->d_prof, &h->prof_bytes, pb);
         if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, pb, st));
@@ -517,15 +523,16 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     }
 
     void* kargs[2] = {(void*)&pl, (void*)&pp};
-    // kernel variants: <batch tile, elements of x per thread, elements of y per thread>
-    const int er = pl.R <= WN_NT ? 1 : (pl.R <= 2 * WN_NT ? 2 : 4);
-    const int eg = pl.G2 <= WN_NT ? 1 : (pl.G2 <= 2 * WN_NT ? 2 : 4);
-    const int var = (er == 1 && eg == 1) ? 0 : ((er <= 2 && eg == 1) ? 1 : 2);
+    // kernel variants: <batch tile, elements of x per thread, elements of y per thread> (128-thread groups)
+    auto efor = [](int K) { return K <= 128 ? 1 : (K <= 256 ? 2 : (K <= 512 ? 4 : 8)); };
+    const int er = efor(pl.R), eg = efor(pl.G2);
+    const int var = (er == 1 && eg == 1) ? 0 : ((er <= 2 && eg <= 2) ? 1 : ((er <= 4 && eg <= 2) ? 2 : 3));
     const void* fn = nullptr;
-#define WN_PICK(BT_)                                                                        \
-    fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 1, 1>                        \
-                  : (var == 1 ? (const void*)wn::wn_persistent_kernel<BT_, 2, 1>            \
-                              : (const void*)wn::wn_persistent_kernel<BT_, 4, 4>)
+#define WN_PICK(BT_)                                                                          \
+    fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 1, 1>                          \
+       : var == 1 ? (const void*)wn::wn_persistent_kernel<BT_, 2, 2>                          \
+       : var == 2 ? (const void*)wn::wn_persistent_kernel<BT_, 4, 2>                          \
+                  : (const void*)wn::wn_persistent_kernel<BT_, 8, 8>
     switch (BT) {
         case 1: WN_PICK(1); break;
         case 2: WN_PICK(2); break;
@@ -533,7 +540,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
         default: WN_PICK(8); break;
     }
 #undef WN_PICK
-    const int ai = bt_index(BT) * 3 + var;
+    const int ai = bt_index(BT) * 4 + var;
     if (!h->attr_set[ai]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
         h->attr_set[ai] = true;
@@ -745,12 +752,14 @@ int32_t wn_sync(void* handle) {
     if (h->d_prof && env_int("WN_PROF", 0)) {
         std::vector<long long> pc(h->prof_bytes / sizeof(long long));
         CUDA_TRY(cudaMemcpy(pc.data(), h->d_prof, h->prof_bytes, cudaMemcpyDeviceToHost));
-        const char* names[8] = {"poll", "gemv_crit", "barrier", "finalize+publish", "deferred", "head+sample", "weights_wait", "x0+noise"};
-        const int P = (int)(pc.size() / 8);
-        for (int i = 0; i < 8; ++i) {
+        const char* names[16] = {"C.poll", "C.gemv", "C.barrier", "C.finalize+publish", "C.acquire+pre", "C.head",
+                                 "C.sample+sync", "C.x0", "D.wait_stash", "D.gemv", "D.finalize", "D.sample+sync",
+                                 "-", "-", "-", "-"};
+        const int P = (int)(pc.size() / 16);
+        for (int i = 0; i < 12; ++i) {
             long long mn = pc[i], mx = pc[i], sum = 0;
-            for (int p = 0; p < P; ++p) { mn = std::min(mn, pc[p * 8 + i]); mx = std::max(mx, pc[p * 8 + i]); sum += pc[p * 8 + i]; }
-            fprintf(stderr, "WN_PROF %-18s mean %12.0f  min %12lld  max %12lld cycles\n", names[i], (double)sum / P, mn, mx);
+            for (int p = 0; p < P; ++p) { mn = std::min(mn, pc[p * 16 + i]); mx = std::max(mx, pc[p * 16 + i]); sum += pc[p * 16 + i]; }
+            fprintf(stderr, "WN_PROF %-20s mean %12.0f  min %12lld  max %12lld cycles\n", names[i], (double)sum / P, mn, mx);
         }
     }
     if (err[0] != 0) {

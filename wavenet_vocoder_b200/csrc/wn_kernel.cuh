@@ -24,11 +24,21 @@
 // then the sampler (mixture.py), which every block evaluates redundantly from the same noise so
 // no further broadcast is needed.
 //
+// Inside a block the 8 compute warps are split in two groups that run concurrently:
+//   critical group (warps 0-3): wait for the broadcast -> current-tap rows -> gate -> publish.
+//       Nothing else sits between two broadcasts.
+//   deferred group (warps 4-7): takes (y_{s-1}, x_{s-1}) from a shared-memory stash left by the critical
+//       group and does everything that is only needed later (queued older-tap products, skip rows).
+// plus one warp that streams weights (TMA) and one that projects the local conditioning.
+//
 // Exchange protocol: every value travels as an 8-byte (value, tag) pair (tag = step*NE+id+1),
 // written with one 8-byte store and polled with 8/16-byte loads, so data and "ready" flag are
-// one atomic word: no fences, no separate barrier, one L2 write + one L2 read per hop.  Each
-// vector is written to `ncopy` replicas so that the P readers do not all hammer the same L2
-// slices.
+// one atomic word: no fences, no separate barrier, one L2 write + one L2 read per hop.  Measured on
+// B200 (profiles/r1_xbench_l2_broadcast.txt): P=128 blocks reading the same lines serialise at the L2
+// slice (~10 cycles per same-line request, ~1650 cycles per round even when the data is already
+// there), and one thread writing several replicas pays ~100-190 cycles per st.relaxed.gpu.  So every
+// vector has `ncopy` replicas, each replica is written by a DIFFERENT thread (the finalizer work is
+// simply done `ncopy` times in parallel), and block p reads replica p % ncopy.
 //
 // Weights: fp32, packed per block by the host ("blobs").  A dedicated warp streams the blobs
 // into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a ring
@@ -147,6 +157,48 @@ __device__ __forceinline__ bool bar_or(bool pred) {
     return r != 0;
 }
 
+// named barrier `ID` over `N` threads, OR-reducing a flag
+template <int ID, int N>
+__device__ __forceinline__ bool bar_or_n(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, %2, %3, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "n"(ID), "n"(N)
+        : "memory");
+    return r != 0;
+}
+
+// NA independent value sets reduced in lock step (the shuffles of different sets overlap)
+template <int NA, int NV>
+__device__ __forceinline__ void reduce_scatter_multi(float (&v)[NA][NV], int lane) {
+    int n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+#pragma unroll
+                for (int i = 0; i < NV / 2; ++i) {
+                    if (i < n) {
+                        const float send = hi ? v[a][i] : v[a][i + n];
+                        const float keep = hi ? v[a][i + n] : v[a][i];
+                        v[a][i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NA; ++a) v[a][0] += __shfl_xor_sync(0xffffffffu, v[a][0], off);
+        }
+    }
+}
+
 template <int NV>
 __device__ __forceinline__ void reduce_scatter(float (&v)[NV], int lane) {
     // butterfly over the 32 lanes; while more than one value is left each step also halves the
@@ -219,16 +271,30 @@ __device__ __noinline__ bool wn_check_abort(volatile int* s_abort, int* err, lon
 }
 
 // ------------------------------------------------------------------------------------------
+#define WN_NTC 128                 // threads of one compute group (4 warps)
+#define WN_GW 4                    // warps per group
+#define WN_DISPATCH_E(EV, ...)                                \
+    switch (EV) {                                             \
+        case 1: { constexpr int E = 1; __VA_ARGS__ } break;   \
+        case 2: { constexpr int E = 2; __VA_ARGS__ } break;   \
+        case 4: { constexpr int E = 4; __VA_ARGS__ } break;   \
+        default: { constexpr int E = 8; __VA_ARGS__ } break;  \
+    }
+
 template <int BT, int ER, int EG>
 struct Engine {
+    static constexpr int NV = 4 * BT;
     const WnPlan& pl;
     const WnPtrs& pp;
     unsigned char* sm;
     int tid, warp, lane, p;
+    int gt, gw;                    // thread / warp index inside the compute group
     uint64_t *bar_full, *bar_empty, *bar_cfull, *bar_cempty;
     volatile int* s_abort;
+    volatile int* s_stash_cnt;     // stashes published by the critical group (monotonic)
+    volatile int* s_ddone_cnt;     // deferred-group warps finished, summed over stages (monotonic)
     int* ringtab;
-    float *xs, *red1, *red2, *sb, *cond, *skipacc, *hs, *noise, *first, *slots;
+    float *xs, *ys, *red1, *red2, *sb, *cond, *skipacc, *hs, *noise, *first, *slots;
     volatile float* ring;
     float* s_in;     // [BT] scalar feedback
     int* s_idx;      // [BT] class feedback
@@ -241,17 +307,22 @@ struct Engine {
         warp = tid >> 5;
         lane = tid & 31;
         p = blockIdx.x;
+        gt = tid & (WN_NTC - 1);
+        gw = warp & (WN_GW - 1);
         const int nslots = pl.nres + pl.nring;
         bar_full = reinterpret_cast<uint64_t*>(sm + pl.sm_bar);
         bar_empty = bar_full + nslots;
         bar_cfull = bar_empty + (pl.nring > 0 ? pl.nring : 1);
         bar_cempty = bar_cfull + 2;
         s_abort = reinterpret_cast<volatile int*>(sm + pl.sm_misc);
+        s_stash_cnt = s_abort + 1;
+        s_ddone_cnt = s_abort + 2;
         s_in = reinterpret_cast<float*>(sm + pl.sm_in);
         s_idx = reinterpret_cast<int*>(s_in + BT);
         s_dense = reinterpret_cast<float*>(s_idx + BT);
         ringtab = reinterpret_cast<int*>(sm + pl.sm_ringtab);
         xs = reinterpret_cast<float*>(sm + pl.sm_xs);
+        ys = xs + 2 * pl.R * BT;
         red1 = reinterpret_cast<float*>(sm + pl.sm_red1);
         red2 = reinterpret_cast<float*>(sm + pl.sm_red2);
         sb = reinterpret_cast<float*>(sm + pl.sm_sb);
@@ -280,16 +351,27 @@ struct Engine {
         }
         return true;
     }
+    // monotonic shared-memory counter (cross-group hand-off inside the block)
+    __device__ __forceinline__ void wait_count(volatile int* cnt, int need, uint32_t what) {
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (*cnt < need) {
+            if (((++spins) & 255u) == 0 && check_abort(what, t0)) {
+                dead = true;
+                return;
+            }
+        }
+        __threadfence_block();
+    }
 
-    // ---- wait for a broadcast vector: thread owns elements k = tid + j*WN_NT.
-    // load_vec issues the loads of one attempt and returns the OR of the tag mismatches.
+    // ---- wait for a broadcast vector: thread owns elements k = gt + j*WN_NTC.
     template <int E>
     __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int K, uint32_t tag,
                                                  float (&x)[E][BT]) {
         uint32_t bad = 0;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            const int k = tid + j * WN_NT;
+            const int k = gt + j * WN_NTC;
             if (k < K) {
                 const uint2* s = src + (size_t)k * BT;
                 if constexpr (BT == 1) {
@@ -344,21 +426,30 @@ struct Engine {
     __device__ __forceinline__ void stash(float* dst, int K, const float (&x)[E][BT]) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            const int k = tid + j * WN_NT;
+            const int k = gt + j * WN_NTC;
             if (k < K) {
 #pragma unroll
                 for (int b = 0; b < BT; ++b) dst[k * BT + b] = x[j][b];
             }
         }
     }
+    template <int E>
+    __device__ __forceinline__ void unstash(const float* src, int K, float (&x)[E][BT]) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = gt + j * WN_NTC;
+#pragma unroll
+            for (int b = 0; b < BT; ++b) x[j][b] = (k < K) ? src[k * BT + b] : 0.f;
+        }
+    }
 
     // ---- one row quad (4 rows x K) times the thread's slice of the input vector, accumulated
     template <int E>
     __device__ __forceinline__ void quad_fma(const float* __restrict__ wq /* [K][4] */, int K,
-                                             const float (&x)[E][BT], float (&acc)[4 * BT]) {
+                                             const float (&x)[E][BT], float (&acc)[NV]) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            const int k = tid + j * WN_NT;
+            const int k = gt + j * WN_NTC;
             if (k < K) {
                 const float4 w4 = *reinterpret_cast<const float4*>(wq + (size_t)k * 4);
 #pragma unroll
@@ -371,33 +462,34 @@ struct Engine {
             }
         }
     }
-    // warp-reduce the 4*BT partial sums of quad `q`; warp w's result lands in red[v*NWARP + w]
-    __device__ __forceinline__ void quad_reduce(float (&acc)[4 * BT], int q, float* __restrict__ red) {
-        constexpr int NV = 4 * BT;
+    // after the warp reduction lane (v << (5-M)) holds value v of the quad; warp gw's partial goes
+    // to red[(q*NV + v)*4 + gw]
+    __device__ __forceinline__ void quad_store(const float (&acc)[NV], int q, float* __restrict__ red) {
         constexpr int M = ilog2c(NV);
-        reduce_scatter<NV>(acc, lane);
-        if ((lane & ((32 >> M) - 1)) == 0) red[(q * NV + (lane >> (5 - M))) * WN_NWARP + warp] = acc[0];
+        if ((lane & ((32 >> M) - 1)) == 0) red[(q * NV + (lane >> (5 - M))) * WN_GW + gw] = acc[0];
     }
+    __device__ __forceinline__ float red_sum(const float* red, int rowidx, int b) const {
+        const int v = (rowidx >> 2) * NV + (rowidx & 3) * BT + b;
+        const float4 a = *reinterpret_cast<const float4*>(red + v * WN_GW);
+        return (a.x + a.y) + (a.z + a.w);
+    }
+    // simple GEMV over NQ quads, two quads per pass so that their shuffle chains overlap
     template <int E>
     __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K, const float (&x)[E][BT],
                                          float* __restrict__ red, int q0 = 0) {
-        for (int q = 0; q < NQ; ++q) {
-            float acc[4 * BT];
+        for (int q = 0; q < NQ; q += 2) {
+            float acc[2][NV];
 #pragma unroll
-            for (int v = 0; v < 4 * BT; ++v) acc[v] = 0.f;
-            quad_fma<E>(w + (size_t)q * K * 4, K, x, acc);
-            quad_reduce(acc, q0 + q, red);
+            for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+            quad_fma<E>(w + (size_t)q * K * 4, K, x, acc[0]);
+            if (q + 1 < NQ) quad_fma<E>(w + (size_t)(q + 1) * K * 4, K, x, acc[1]);
+            reduce_scatter_multi<2, NV>(acc, lane);
+            quad_store(acc[0], q0 + q, red);
+            if (q + 1 < NQ) quad_store(acc[1], q0 + q + 1, red);
         }
     }
-    __device__ __forceinline__ float red_sum(const float* red, int rowidx, int b) const {
-        const int v = (rowidx >> 2) * (4 * BT) + (rowidx & 3) * BT + b;
-        const float4* r = reinterpret_cast<const float4*>(red + v * WN_NWARP);
-        const float4 a = r[0], c = r[1];
-        return ((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w));
-    }
-    __device__ __forceinline__ void publish(int elem_off, int row, int b, float v, uint32_t tag) {
-        uint2* dst = pp.xbuf + ((size_t)(elem_off + row) * BT + b);
-        for (int c = 0; c < pl.ncopy; ++c) st_pair(dst + (size_t)c * pl.copy_stride_pairs, v, tag);
+    __device__ __forceinline__ void publish(int elem, int b, int copy, float v, uint32_t tag) {
+        st_pair(pp.xbuf + (size_t)copy * pl.copy_stride_pairs + ((size_t)elem * BT + b), v, tag);
     }
 
     // ---- weight slots
@@ -668,20 +760,22 @@ struct Engine {
     }
 
     // ======================================================================================
-    // compute warps
+    // compute groups
     // ======================================================================================
-    __device__ __forceinline__ static int efor(int K) { return K <= WN_NT ? 1 : (K <= 2 * WN_NT ? 2 : 4); }
+    __device__ __forceinline__ static int efor(int K) {
+        return K <= WN_NTC ? 1 : (K <= 2 * WN_NTC ? 2 : (K <= 4 * WN_NTC ? 4 : 8));
+    }
 
+    // x_0 = first 1x1 conv of the fed-back sample (wavenet.py:308); every block computes all of it
     __device__ __forceinline__ void make_x0(float (&x)[ER][BT]) {
         const int R = pl.R, O = pl.O;
 #pragma unroll
         for (int j = 0; j < ER; ++j) {
-            const int k = tid + j * WN_NT;
+            const int k = gt + j * WN_NTC;
 #pragma unroll
             for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
             if (k < R) {
                 if (pl.input_kind == 0) {
-                    // wavenet.py:308  first 1x1 conv on a scalar: w*x + b
 #pragma unroll
                     for (int b = 0; b < BT; ++b) x[j][b] = fmaf(first[k], s_in[b], first[R + k]);
                 } else {
@@ -701,18 +795,8 @@ struct Engine {
                 }
             }
         }
-        stash<ER>(xs, R, x);
     }
-
-#define WN_DISPATCH_E(EV, ...)                                \
-    switch (EV) {                                             \
-        case 1: { constexpr int E = 1; __VA_ARGS__ } break;   \
-        case 2: { constexpr int E = 2; __VA_ARGS__ } break;   \
-        default: { constexpr int E = 4; __VA_ARGS__ } break;  \
-    }
-
-    // ---- finalizers (64-thread groups, see wn_plan.h) ------------------------------------
-    // everything of z_s that does not depend on this stage's broadcast, for gate pair `fr`
+    // everything of z_l that does not depend on this stage's broadcast, for gate pair `fr`
     __device__ __forceinline__ void gate_pre(int t, int l, int fr, int fb, float& pre_a, float& pre_b) {
         const int RA4 = pl.RA4, kw = pl.kw, ra = 2 * fr, rb = 2 * fr + 1;
         pre_a = sb[((size_t)l * RA4 + ra) * BT + fb];
@@ -729,32 +813,12 @@ struct Engine {
             pre_b += rp[rb * BT + fb];
         }
     }
-    // gate outputs of layer l -> y part of exchange l
-    __device__ __forceinline__ void finalize_gates(int t, int l, int y0, int ny, uint32_t tag, float pre_a, float pre_b) {
-        const int n = ny * BT;
-        for (int f = tid - WN_FIN_Y; f < n; f += WN_FIN_W) {
-            const int fr = f / BT, fb = f % BT;
-            if (f != tid - WN_FIN_Y) gate_pre(t, l, fr, fb, pre_a, pre_b);    // extra items: not pre-summed
-            const float a = red_sum(red1, 2 * fr, fb) + pre_a;
-            const float g = red_sum(red1, 2 * fr + 1, fb) + pre_b;
-            const float yv = tanhf(a) * (1.0f / (1.0f + expf(-g)));            // modules.py:154
-            publish(pl.ex_yx + l * (pl.G2 + pl.R), y0 + fr, fb, yv, tag);
-        }
-    }
-    // queued older-tap products of `layer` (partials in red2 buffer `buf`) -> history ring
-    __device__ __forceinline__ void finalize_ring(int t, int layer, const float* buf) {
-        const int kw = pl.kw, n = (kw - 1) * pl.RA * BT;
-        for (int f = tid - WN_FIN_RING; f < n; f += WN_FIN_W) {
-            const int dr = f / BT, db = f % BT, tap = dr / pl.RA, rr = dr % pl.RA;
-            const float v = red_sum(buf, dr, db);
-            const int off = ringtab[(layer * (kw - 1) + tap) * 2], D = ringtab[(layer * (kw - 1) + tap) * 2 + 1];
-            ring[((size_t)off + (uint32_t)t % (uint32_t)D) * pl.RA4 * BT + rr * BT + db] = v;
-        }
-    }
 
-    __device__ void compute_loop() {
-        const int L = pl.L, R = pl.R, G2 = pl.G2, S = pl.S, O = pl.O, kw = pl.kw, T = pp.T;
-        const int P = pl.P;
+    // --------------------------------------------------------------------------------------
+    // critical group (warps 0-3)
+    // --------------------------------------------------------------------------------------
+    __device__ void crit_loop() {
+        const int L = pl.L, R = pl.R, G2 = pl.G2, S = pl.S, O = pl.O, T = pp.T, P = pl.P, ncopy = pl.ncopy;
         int y0, ny, x0r, nx, s0, ns, a0, na, b0, nb;
         wn_part(G2, P, p, y0, ny);
         wn_part(R, P, p, x0r, nx);
@@ -762,224 +826,307 @@ struct Engine {
         wn_part(S, P, p, a0, na);
         wn_part(O, P, p, b0, nb);
         const int ES = efor(S), EO = efor(O);
-        const uint2* xin = pp.xbuf + (size_t)(p % pl.ncopy) * pl.copy_stride_pairs;
+        const uint2* xin = pp.xbuf + (size_t)(p % ncopy) * pl.copy_stride_pairs;
         const uint32_t NEID = (uint32_t)L + 3u;
         const int YX = G2 + R;
         const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
-        const int red2B_off = pl.NQ_D * 4 * BT * WN_NWARP;    // skip partials follow the tap partials
-        float* skb0 = skipacc + pl.NSm * BT;                  // skip bias of the layer whose rows are pending,
-        const int skbN = 4 * pl.NQ_BS;                        // double-buffered by stage parity
-        const bool finY = (tid >= WN_FIN_Y && tid < WN_FIN_Y + WN_FIN_W);
-        const bool finX = (tid >= WN_FIN_X && tid < WN_FIN_X + WN_FIN_W);
-        const bool finR = (tid >= WN_FIN_RING && tid < WN_FIN_RING + WN_FIN_W);
-        const bool finS = (tid >= WN_FIN_SKIP && tid < WN_FIN_SKIP + WN_FIN_W);
-        const int f0r = (tid - WN_FIN_Y) / BT, f0b = (tid - WN_FIN_Y) % BT;   // first gate item of a Y-group thread
+        const int NQ_A = pl.NQ_A, NQ_BO = pl.NQ_BO, nqc = NQ_A + NQ_BO;
+        // finalizer roles: threads [0,64) publish gate outputs (and skip / head rows), [64,128) the
+        // residual rows; local index u -> (item, replica)
+        const int fl = gt & 63;
+        const bool grpA = gt < 64;
+        auto role = [&](int nitems, int& item, int& copy) {
+            item = -1; copy = 0;
+            if (nitems > 0 && fl < nitems * ncopy) { item = fl % nitems; copy = fl / nitems; }
+        };
+        int it_y, cp_y, it_x, cp_x, it_s, cp_s, it_a, cp_a, it_b, cp_b;
+        role(ny * BT, it_y, cp_y);
+        role(nx * BT, it_x, cp_x);
+        role(ns * BT, it_s, cp_s);
+        role(na * BT, it_a, cp_a);
+        role(nb * BT, it_b, cp_b);
+        if (!grpA) it_y = it_s = it_a = it_b = -1;
+        if (grpA) it_x = -1;
         float xr[ER][BT], yr[EG][BT];
         const bool prof = (pp.prof != nullptr) && tid == 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
 #define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
-
-        // feedback for step 0 (wavenet.py:281-301)
-        if (tid < BT) {
-            const int b = tid;
-            float v = 0.f;
-            int idx = -1;
-            if (b < pp.B) {
-                if (pl.input_kind == 0) {
-                    if (pp.T_test > 0) v = pp.test_scalar[(size_t)b * pp.T_test];
-                    else if (pp.initial) v = pp.initial[b];
-                } else {
-                    if (pp.T_test > 0) idx = pp.test_index ? pp.test_index[(size_t)b * pp.T_test] : -1;
-                    else idx = pp.initial_index;
-                }
-            } else if (pl.input_kind != 0) idx = 0;
-            s_in[b] = v;
-            s_idx[b] = idx;
-        }
-        if (pl.input_kind != 0 && pp.T_test > 0 && pp.test_dense != nullptr) {
-            for (int i = tid; i < BT * O; i += WN_NT) {
-                const int b = i / O, o = i % O;
-                s_dense[i] = (b < pp.B) ? pp.test_dense[((size_t)b * pp.T_test) * O + o] : 0.f;
-            }
-        }
-        if (bar_or(false)) return;
+        int nstash = 0;      // stashes published so far == deferred stages started
+        int ndone = 0;       // deferred stages this group has waited for
 
         for (int t = 0; t < T; ++t) {
             const uint32_t tagbase = (uint32_t)t * NEID + 1u;
             if (prof) tc = clock64();
-            if (pl.C > 0) {
-                if (!wait_bar(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
-            }
-            make_x0(xr);
-            if (warp < BT) fetch_noise(t, warp);
-            WN_TICK(7);
-            // ------------------------------------------------------------ stage 0: layer 0 from x_0
-            {
-                const float* W = acquire_blob(t, 0);
-                WN_TICK(6);
-                float pre_a = 0.f, pre_b = 0.f;
-                if (finY && f0r < ny) gate_pre(t, 0, f0r, f0b, pre_a, pre_b);
-                gemv<ER>(W + pl.fb_Zx, pl.NQ_A, R, xr, red1);
-                WN_TICK(1);
-                if (bar_or(dead)) return;
-                WN_TICK(2);
-                if (finY) finalize_gates(t, 0, y0, ny, tagbase + wn_eid_yx(0), pre_a, pre_b);
-                release_blob(t, 0);
-                WN_TICK(3);
-            }
-            // ------------------------------------------------------------ stages 1..L-1
-            for (int s = 1; s < L; ++s) {
-                const float* W = acquire_blob(t, s);
-                WN_TICK(6);
-                float pre_a = 0.f, pre_b = 0.f;
-                if (finY && f0r < ny) gate_pre(t, s, f0r, f0b, pre_a, pre_b);
+            bool step_dead = false;
+            do {
+                if (pl.C > 0) {
+                    if (!wait_bar(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
+                }
+                make_x0(xr);
+                WN_TICK(7);
+                // ------------------------------------------------------------ stage 0: layer 0 from x_0
                 {
-                    const uint2* src = xin + (size_t)(pl.ex_yx + (s - 1) * YX) * BT;
-                    const uint32_t tag = tagbase + wn_eid_yx(s - 1);
-                    if (s >= 2) {
-                        poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
-                        stash<ER>(xs, R, xr);
-                    } else {
-                        poll_vec<EG>(src, G2, tag, yr);       // x_0 is already in registers
+                    const float* W = acquire_blob(t, 0);
+                    float pre_a = 0.f, pre_b = 0.f;
+                    if (it_y >= 0) gate_pre(t, 0, it_y / BT, it_y % BT, pre_a, pre_b);
+                    float* r1 = red1;                                   // partials buffers alternate by stage
+                    gemv<ER>(W + pl.fb_Zx, NQ_A, R, xr, r1);
+                    WN_TICK(1);
+                    if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                    WN_TICK(2);
+                    if (it_y >= 0) {
+                        const int fr = it_y / BT, fb = it_y % BT;
+                        const float a = red_sum(r1, 2 * fr, fb) + pre_a;
+                        const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
+                        publish(pl.ex_yx + y0 + fr, fb, cp_y, tanhf(a) * (1.0f / (1.0f + expf(-g))), tagbase + wn_eid_yx(0));
                     }
+                    release_blob(t, 0);
+                    WN_TICK(3);
+                }
+                // ------------------------------------------------------------ stages 1..L-1
+                for (int s = 1; s < L; ++s) {
+                    const float* W = acquire_blob(t, s);
+                    float pre_a = 0.f, pre_b = 0.f;
+                    if (it_y >= 0) gate_pre(t, s, it_y / BT, it_y % BT, pre_a, pre_b);
+                    WN_TICK(4);
+                    {
+                        const uint2* src = xin + (size_t)(pl.ex_yx + (s - 1) * YX) * BT;
+                        const uint32_t tag = tagbase + wn_eid_yx(s - 1);
+                        if (s >= 2) poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
+                        else poll_vec<EG>(src, G2, tag, yr);          // x_0 is already in registers
+                    }
+                    WN_TICK(0);
+                    float* xst = xs + (size_t)(s & 1) * R * BT;
+                    float* r1 = red1 + (size_t)(s & 1) * pl.red1_floats;
+                    stash<ER>(xst, R, xr);
+                    stash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
+                    // gate pre-activations of layer s (quads [0,NQ_A)) and residual rows x_s (quads [NQ_A,nqc))
+                    for (int q = 0; q < nqc; q += 2) {
+                        float acc[2][NV];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int qq = q + h;
+                            if (qq < NQ_A) {
+                                quad_fma<EG>(W + pl.lb_Zy + (size_t)qq * G2 * 4, G2, yr, acc[h]);
+                                quad_fma<ER>(W + pl.lb_Zx + (size_t)qq * R * 4, R, xr, acc[h]);
+                            } else if (qq < nqc) {
+                                quad_fma<EG>(W + pl.lb_Xo + (size_t)(qq - NQ_A) * G2 * 4, G2, yr, acc[h]);
+                            }
+                        }
+                        reduce_scatter_multi<2, NV>(acc, lane);
+                        quad_store(acc[0], q, r1);
+                        if (q + 1 < nqc) quad_store(acc[1], q + 1, r1);
+                    }
+                    WN_TICK(1);
+                    if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                    if (gt == 0) {          // stash complete (the barrier ordered every thread's writes)
+                        __threadfence_block();
+                        *s_stash_cnt = nstash + 1;
+                    }
+                    ++nstash;
+                    WN_TICK(2);
+                    const uint32_t tag = tagbase + wn_eid_yx(s);
+                    if (it_y >= 0) {
+                        const int fr = it_y / BT, fb = it_y % BT;
+                        const float a = red_sum(r1, 2 * fr, fb) + pre_a;
+                        const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
+                        publish(pl.ex_yx + s * YX + y0 + fr, fb, cp_y, tanhf(a) * (1.0f / (1.0f + expf(-g))), tag);   // modules.py:154
+                    }
+                    if (it_x >= 0) {
+                        // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
+                        const int fr = it_x / BT, fb = it_x % BT;
+                        const float o = red_sum(r1, NQ_A * 4 + fr, fb) + W[pl.lb_xb + fr];
+                        publish(pl.ex_yx + s * YX + G2 + x0r + fr, fb, cp_x, (o + xst[(x0r + fr) * BT + fb]) * RSQRT2, tag);
+                    }
+                    release_blob(t, s);
+                    // the stash of stage s+1 reuses the buffer of stage s-1: the deferred group must be done with it
+                    if (s >= 2) { wait_count(s_ddone_cnt, WN_GW * (ndone + 1), 0x08000000u); ++ndone; }
+                    WN_TICK(3);
+                }
+                if (step_dead) break;
+                // ------------------------------------------------------------ stage L: skip of the last layer
+                const float* H = acquire_blob(t, L);
+                {
+                    const uint2* src = xin + (size_t)(pl.ex_yx + (L - 1) * YX) * BT;
+                    const uint32_t tag = tagbase + wn_eid_yx(L - 1);
+                    if (L >= 2) poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
+                    else poll_vec<EG>(src, G2, tag, yr);
                 }
                 WN_TICK(0);
-                // critical: gate pre-activations of layer s and the residual rows x_s
-                for (int q = 0; q < pl.NQ_A; ++q) {
-                    float acc[4 * BT];
-#pragma unroll
-                    for (int v = 0; v < 4 * BT; ++v) acc[v] = 0.f;
-                    quad_fma<EG>(W + pl.lb_Zy + (size_t)q * G2 * 4, G2, yr, acc);
-                    quad_fma<ER>(W + pl.lb_Zx + (size_t)q * R * 4, R, xr, acc);
-                    quad_reduce(acc, q, red1);
-                }
-                gemv<EG>(W + pl.lb_Xo, pl.NQ_BO, G2, yr, red1, pl.NQ_A);
+                stash<ER>(xs + (size_t)(L & 1) * R * BT, R, xr);
+                float* r1 = red1 + (size_t)(L & 1) * pl.red1_floats;
+                gemv<EG>(H + pl.tb_Sk, pl.NQ_BS, G2, yr, r1);
                 WN_TICK(1);
-                if (bar_or(dead)) return;
-                WN_TICK(2);
-                const uint32_t tag = tagbase + wn_eid_yx(s);
-                if (finY) finalize_gates(t, s, y0, ny, tag, pre_a, pre_b);
-                if (finX) {
-                    // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
-                    for (int f = tid - WN_FIN_X; f < nx * BT; f += WN_FIN_W) {
-                        const int fr = f / BT, fb = f % BT;
-                        const float o = red_sum(red1, pl.NQ_A * 4 + fr, fb) + W[pl.lb_xb + fr];
-                        const float xn = (o + xs[(x0r + fr) * BT + fb]) * RSQRT2;
-                        publish(pl.ex_yx + s * YX + G2, x0r + fr, fb, xn, tag);
-                    }
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (gt == 0) {
+                    __threadfence_block();
+                    *s_stash_cnt = nstash + 1;
                 }
-                const float* prev = red2 + (size_t)((s - 1) & 1) * pl.red2_floats;
-                if (finR && s >= 2 && kw > 1) finalize_ring(t, s - 2, prev);
-                if (finS) {
-                    if (s >= 2) {
-                        // skip rows of layer s-2, accumulated in layer order (wavenet.py:312)
-                        for (int f = tid - WN_FIN_SKIP; f < ns * BT; f += WN_FIN_W) {
-                            const int fr = f / BT, fb = f % BT;
-                            const float h = red_sum(prev + red2B_off, fr, fb) + skb0[((s - 1) & 1) * skbN + fr];
-                            skipacc[f] = (s == 2) ? h : skipacc[f] + h;
-                        }
-                    }
-                    for (int r = tid - WN_FIN_SKIP; r < ns; r += WN_FIN_W)
-                        skb0[(s & 1) * skbN + r] = W[pl.lb_sb + r];                  // bias of layer s-1
+                ++nstash;
+                if (pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // every gate of step t has read cond[t&1]
+                // skip rows of layers 0..L-2 were accumulated by the deferred group: wait for its stage L-1
+                if (L >= 2) { wait_count(s_ddone_cnt, WN_GW * (ndone + 1), 0x08000001u); ++ndone; }
+                WN_TICK(2);
+                if (it_s >= 0) {
+                    // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
+                    const int fr = it_s / BT, fb = it_s % BT;
+                    float tot = red_sum(r1, fr, fb) + H[pl.tb_sb + fr];
+                    if (L >= 2) tot = skipacc[it_s] + tot;
+                    publish(pl.ex_sk + s0 + fr, fb, cp_s, fmaxf(tot * pl.skip_scale, 0.f), tagbase + wn_eid_sk(pl));
                 }
                 WN_TICK(3);
-                // deferred: older taps and skip rows of layer s-1
-                float* cur = red2 + (size_t)(s & 1) * pl.red2_floats;
-                if (kw > 1) gemv<ER>(W + pl.lb_Td, pl.NQ_D, R, xr, cur);
-                gemv<EG>(W + pl.lb_Sk, pl.NQ_BS, G2, yr, cur + red2B_off);
-                release_blob(t, s);
-                WN_TICK(4);
-            }
-            // ------------------------------------------------------------ stage L: skip of the last layer
-            const float* H = acquire_blob(t, L);
+                // ---------------------------------------------------------------- head (wavenet.py:315-319)
+                float* r1a = red1 + (size_t)((L + 1) & 1) * pl.red1_floats;
+                if (na > 0) {
+                    const uint2* src = xin + (size_t)pl.ex_sk * BT;
+                    WN_DISPATCH_E(ES, { float h[E][BT];
+                                        poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), h);
+                                        gemv<E>(H + pl.tb_Ha, pl.NQ_HA, S, h, r1a); });
+                }
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (it_a >= 0) {
+                    const int fr = it_a / BT, fb = it_a % BT;
+                    publish(pl.ex_h1 + a0 + fr, fb, cp_a, fmaxf(red_sum(r1a, fr, fb) + H[pl.tb_Hab + fr], 0.f), tagbase + wn_eid_h1(pl));
+                }
+                if (nb > 0) {
+                    const uint2* src = xin + (size_t)pl.ex_h1 * BT;
+                    WN_DISPATCH_E(ES, { float h[E][BT];
+                                        poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), h);
+                                        gemv<E>(H + pl.tb_Hb, pl.NQ_HB, S, h, r1); });
+                }
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (it_b >= 0) {
+                    const int fr = it_b / BT, fb = it_b % BT;
+                    publish(pl.ex_h2 + b0 + fr, fb, cp_b, red_sum(r1, fr, fb) + H[pl.tb_Hbb + fr], tagbase + wn_eid_h2(pl));
+                }
+                release_blob(t, L);
+                {
+                    const uint2* src = xin + (size_t)pl.ex_h2 * BT;
+                    WN_DISPATCH_E(EO, { float h[E][BT];
+                                        poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), h);
+                                        stash<E>(hs, O, h); });
+                }
+                WN_TICK(5);
+            } while (false);
+            // ---- both groups meet: sampler (one warp per utterance), then the next step
+            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            // the deferred group finished its stage L before this barrier
+            if (L >= 1) ++ndone;
+            step_tail(t);
+            if (bar_or_n<3, WN_NT>(false)) return;
             WN_TICK(6);
-            {
-                const uint2* src = xin + (size_t)(pl.ex_yx + (L - 1) * YX) * BT;
-                const uint32_t tag = tagbase + wn_eid_yx(L - 1);
-                if (L >= 2) {
-                    poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
-                } else {
-                    poll_vec<EG>(src, G2, tag, yr);
-                }
-            }
-            WN_TICK(0);
-            gemv<EG>(H + pl.tb_Sk, pl.NQ_BS, G2, yr, red1);
-            WN_TICK(1);
-            if (bar_or(dead)) return;
-            WN_TICK(2);
-            if (pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // every gate of step t has read cond[t&1]
-            {
-                const float* prev = red2 + (size_t)((L - 1) & 1) * pl.red2_floats;
-                if (finS) {
-                    // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
-                    for (int f = tid - WN_FIN_SKIP; f < ns * BT; f += WN_FIN_W) {
-                        const int fr = f / BT, fb = f % BT;
-                        float tot = red_sum(red1, fr, fb) + H[pl.tb_sb + fr];
-                        if (L >= 2) {
-                            const float pend = red_sum(prev + red2B_off, fr, fb) + skb0[((L - 1) & 1) * skbN + fr];
-                            tot = ((L >= 3) ? skipacc[f] + pend : pend) + tot;
-                        }
-                        publish(pl.ex_sk, s0 + fr, fb, fmaxf(tot * pl.skip_scale, 0.f), tagbase + wn_eid_sk(pl));
-                    }
-                }
-                if (finR && L >= 2 && kw > 1) finalize_ring(t, L - 2, prev);
-            }
-            WN_TICK(3);
-            float* tailbuf = red2 + (size_t)(L & 1) * pl.red2_floats;
-            if (kw > 1) gemv<ER>(H + pl.tb_Td, pl.NQ_D, R, xr, tailbuf);      // older taps of layer L-1
-            WN_TICK(4);
-            // ---------------------------------------------------------------- head (wavenet.py:315-319)
-            if (na > 0) {
-                const uint2* src = xin + (size_t)pl.ex_sk * BT;
-                WN_DISPATCH_E(ES, { float h[E][BT];
-                                    poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), h);
-                                    gemv<E>(H + pl.tb_Ha, pl.NQ_HA, S, h, red1); });
-            }
-            if (bar_or(dead)) return;                                                // S3
-            if (finY) {
-                for (int f = tid - WN_FIN_Y; f < na * BT; f += WN_FIN_W) {
-                    const int fr = f / BT, fb = f % BT;
-                    const float h1 = fmaxf(red_sum(red1, fr, fb) + H[pl.tb_Hab + fr], 0.f);
-                    publish(pl.ex_h1, a0 + fr, fb, h1, tagbase + wn_eid_h1(pl));
-                }
-            }
-            if (finR && kw > 1) finalize_ring(t, L - 1, tailbuf);
-            if (nb > 0) {
-                const uint2* src = xin + (size_t)pl.ex_h1 * BT;
-                WN_DISPATCH_E(ES, { float h[E][BT];
-                                    poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), h);
-                                    gemv<E>(H + pl.tb_Hb, pl.NQ_HB, S, h, red1); });
-            }
-            if (bar_or(dead)) return;                                                // S4
-            if (finY) {
-                for (int f = tid - WN_FIN_Y; f < nb * BT; f += WN_FIN_W) {
-                    const int fr = f / BT, fb = f % BT;
-                    const float h2 = red_sum(red1, fr, fb) + H[pl.tb_Hbb + fr];
-                    publish(pl.ex_h2, b0 + fr, fb, h2, tagbase + wn_eid_h2(pl));
-                }
-            }
-            release_blob(t, L);
-            {
-                const uint2* src = xin + (size_t)pl.ex_h2 * BT;
-                WN_DISPATCH_E(EO, { float h[E][BT];
-                                    poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), h);
-                                    stash<E>(hs, O, h); });
-            }
-            if (bar_or(dead)) return;                                                // S5
-            if (p == 0 && pp.params_out != nullptr) {
-                for (int i = tid; i < O * BT; i += WN_NT) {
-                    const int o = i / BT, b = i % BT;
-                    if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
-                }
-                // the softmax sampler overwrites hs in place: finish the copy first (block-uniform)
-                if (pl.head_kind == 2) { if (bar_or(false)) return; }
-            }
-            if (warp < BT) sample_utt(t, warp);
-            if (bar_or(false)) return;                                               // S6
-            WN_TICK(5);
         }
         if (prof) {
-            for (int i = 0; i < 8; ++i) pp.prof[(size_t)p * 8 + i] = pc[i];
+            for (int i = 0; i < 8; ++i) pp.prof[(size_t)p * 16 + i] = pc[i];
+        }
+#undef WN_TICK
+    }
+
+    // head outputs are in hs: optional dump, sampling, feedback for the next step (all 8 compute warps)
+    __device__ __forceinline__ void step_tail(int t) {
+        const int O = pl.O, T = pp.T;
+        if (p == 0 && pp.params_out != nullptr) {
+            for (int i = tid; i < O * BT; i += WN_NT) {
+                const int o = i / BT, b = i % BT;
+                if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
+            }
+            // the softmax sampler overwrites hs in place: finish the copy first (block-uniform)
+            if (pl.head_kind == 2) bar_or_n<3, WN_NT>(false);
+        }
+        if (warp < BT) {
+            sample_utt(t, warp);
+            if (t + 1 < T) fetch_noise(t + 1, warp);
+        }
+    }
+
+    // --------------------------------------------------------------------------------------
+    // deferred group (warps 4-7): queued older-tap products and skip rows, one stage behind
+    // --------------------------------------------------------------------------------------
+    __device__ void def_loop() {
+        const int L = pl.L, R = pl.R, G2 = pl.G2, T = pp.T, P = pl.P, kw = pl.kw;
+        int s0, ns;
+        wn_part(pl.S, P, p, s0, ns);
+        const int NQ_D = pl.NQ_D, NQ_BS = pl.NQ_BS, nqd = (kw > 1 ? NQ_D : 0) + NQ_BS;
+        const int qoff = (kw > 1 ? NQ_D : 0);
+        const int nring_items = (kw - 1) * pl.RA * BT, nskip_items = ns * BT;
+        float xr[ER][BT], yr[EG][BT];
+        const bool prof = (pp.prof != nullptr) && gt == 0;
+        long long pc[4] = {0, 0, 0, 0}, tc = 0;
+#define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
+        int nstash = 0;
+
+        // one deferred stage: `Td` = older taps of `layer` (uses x), `Sk`/`skb` = skip rows of `layer`
+        // (uses y; nullptr in the tail stage, where the critical group evaluates them itself)
+        auto stage = [&](int t, int s, int layer, const float* Td, const float* Sk, const float* skb) {
+            wait_count(s_stash_cnt, nstash + 1, 0x04000000u);
+            ++nstash;
+            WN_TICK(0);
+            unstash<ER>(xs + (size_t)(s & 1) * R * BT, R, xr);
+            if (Sk) unstash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
+            float* red = red2 + (size_t)(s & 1) * pl.red2_floats;
+            const int nq = Sk ? nqd : qoff;
+            for (int q = 0; q < nq; q += 2) {
+                float acc[2][NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qq = q + h;
+                    if (qq < qoff) quad_fma<ER>(Td + (size_t)qq * R * 4, R, xr, acc[h]);
+                    else if (qq < nq) quad_fma<EG>(Sk + (size_t)(qq - qoff) * G2 * 4, G2, yr, acc[h]);
+                }
+                reduce_scatter_multi<2, NV>(acc, lane);
+                quad_store(acc[0], q, red);
+                if (q + 1 < nq) quad_store(acc[1], q + 1, red);
+            }
+            WN_TICK(1);
+            const bool d = bar_or_n<2, WN_NTC>(dead);
+            if (!d) {
+                // older-tap products of `layer` -> history ring (consumed at steps t+d, t+2d, conv.py:32-44)
+                for (int f = gt; f < nring_items; f += WN_NTC) {
+                    const int dr = f / BT, db = f % BT, tap = dr / pl.RA, rr = dr % pl.RA;
+                    const int off = ringtab[(layer * (kw - 1) + tap) * 2], D = ringtab[(layer * (kw - 1) + tap) * 2 + 1];
+                    ring[((size_t)off + (uint32_t)t % (uint32_t)D) * pl.RA4 * BT + rr * BT + db] = red_sum(red, dr, db);
+                }
+                // skip rows, accumulated in layer order (wavenet.py:312)
+                if (Sk) {
+                    for (int f = gt; f < nskip_items; f += WN_NTC) {
+                        const int fr = f / BT, fb = f % BT;
+                        const float h = red_sum(red, qoff * 4 + fr, fb) + skb[fr];
+                        skipacc[f] = (layer == 0) ? h : skipacc[f] + h;
+                    }
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd((int*)s_ddone_cnt, 1);
+            WN_TICK(2);
+            return d;
+        };
+
+        for (int t = 0; t < T; ++t) {
+            if (prof) tc = clock64();
+            bool step_dead = false;
+            release_blob(t, 0);                       // stage 0 has no deferred work
+            for (int s = 1; s < L && !step_dead; ++s) {
+                const float* W = acquire_blob(t, s);
+                step_dead = stage(t, s, s - 1, W + pl.lb_Td, W + pl.lb_Sk, W + pl.lb_sb);
+                release_blob(t, s);
+            }
+            if (!step_dead) {
+                const float* H = acquire_blob(t, L);
+                step_dead = stage(t, L, L - 1, H + pl.tb_Td, nullptr, nullptr);
+                release_blob(t, L);
+            }
+            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            step_tail(t);
+            if (bar_or_n<3, WN_NT>(false)) return;
+            WN_TICK(3);
+        }
+        if (prof) {
+            for (int i = 0; i < 4; ++i) pp.prof[(size_t)p * 16 + 8 + i] = pc[i];
         }
 #undef WN_TICK
     }
@@ -1003,6 +1150,8 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
             mbar_init(&eng.bar_cempty[i], 1);
         }
         *eng.s_abort = 0;
+        *eng.s_stash_cnt = 0;
+        *eng.s_ddone_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero the history (== the reference's zero-initialised queue, conv.py:35-36) and scratch
@@ -1010,14 +1159,14 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         const size_t n = (size_t)pl.ring_pos_total * pl.RA4 * BT;
         for (size_t i = tid; i < n; i += WN_NTHREADS) eng.ring[i] = 0.f;
     }
-    for (int i = tid; i < pl.NSm * BT + 8 * pl.NQ_BS; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
+    for (int i = tid; i < pl.NSm * BT + 4; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
     for (int i = tid; i < pl.L * (pl.kw - 1) * 2; i += WN_NTHREADS) eng.ringtab[i] = pp.ringtab[i];
     for (int k = tid; k < pl.R; k += WN_NTHREADS) {
         eng.first[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
         eng.first[pl.R + k] = pp.first_b[k];
     }
     {
-        // static part of the pre-activation: conv bias + global-conditioning projection
+        // static part of the pre-activation: (folded) conv bias + global-conditioning projection
         // (modules.py:148-152 recomputes Wg.g every step although g is constant; fold it once)
         int y0, ny;
         wn_part(pl.G2, pl.P, p, y0, ny);
@@ -1036,8 +1185,32 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
             eng.sb[i] = v;
         }
     }
-    __syncthreads();
+    // feedback for step 0 (wavenet.py:281-301)
+    if (tid < BT) {
+        const int b = tid;
+        float v = 0.f;
+        int idx = -1;
+        if (b < pp.B) {
+            if (pl.input_kind == 0) {
+                if (pp.T_test > 0) v = pp.test_scalar[(size_t)b * pp.T_test];
+                else if (pp.initial) v = pp.initial[b];
+            } else {
+                if (pp.T_test > 0) idx = pp.test_index ? pp.test_index[(size_t)b * pp.T_test] : -1;
+                else idx = pp.initial_index;
+            }
+        } else if (pl.input_kind != 0) idx = 0;
+        eng.s_in[b] = v;
+        eng.s_idx[b] = idx;
+    }
+    if (pl.input_kind != 0 && pp.T_test > 0 && pp.test_dense != nullptr) {
+        for (int i = tid; i < BT * pl.O; i += WN_NTHREADS) {
+            const int b = i / pl.O, o = i % pl.O;
+            eng.s_dense[i] = (b < pp.B) ? pp.test_dense[((size_t)b * pp.T_test) * pl.O + o] : 0.f;
+        }
+    }
     const int warp = tid >> 5;
+    if (warp < BT && warp < WN_NWARP) eng.fetch_noise(0, warp);
+    __syncthreads();
     if (warp == WN_NWARP) {
         eng.tma_loop();
         return;
@@ -1046,7 +1219,8 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         if (pl.C > 0) eng.cond_loop();
         return;
     }
-    eng.compute_loop();
+    if (warp < WN_GW) eng.crit_loop();
+    else eng.def_loop();
 }
 
 // gbias[b][l][row] = Wg_l[row,:] . g_b   (modules.py:148-152), once per call

@@ -23,7 +23,7 @@
 #define WN_NWARP (WN_NT / 32)
 #define WN_AUX_WARPS 2            // +1 weight-streaming (TMA) warp, +1 conditioning warp
 #define WN_NTHREADS (WN_NT + 32 * WN_AUX_WARPS)
-#define WN_MAXE 4                 // a stage input vector has at most WN_MAXE*WN_NT entries
+#define WN_MAXE 8                 // a stage input vector has at most WN_MAXE*128 entries (128-thread groups)
 #define WN_MAX_BT 8               // utterances processed together by one launch
 #define WN_MAX_CI 4               // local-conditioning channels <= 32*WN_MAX_CI
 
@@ -78,6 +78,7 @@ struct WnPlan {
     // ---- shared memory map (byte offsets)
     int sm_bar, sm_misc, sm_ringtab, sm_xs, sm_red1, sm_red2, sm_sb, sm_cond, sm_skipacc, sm_hs,
         sm_noise, sm_in, sm_first, sm_ring, sm_slots, smem_bytes;
+    int red1_floats;            // one of the two critical-partials buffers (alternating by stage)
     int red2_floats;            // one of the two deferred-partials buffers
     float skip_scale;           // sqrt(1/L), wavenet.py:313
 };
@@ -103,9 +104,3 @@ WN_HD long long wn_blob_off(const WnPlan& pl, int i) {
 WN_HD int wn_blob_floats(const WnPlan& pl, int i) {
     return i == 0 ? pl.fb_floats : (i < pl.L ? pl.lb_floats : pl.tb_floats);
 }
-// finalizer thread groups (64 threads each): gate outputs | residual rows | queued taps | skip rows
-#define WN_FIN_Y 0
-#define WN_FIN_X 64
-#define WN_FIN_RING 128
-#define WN_FIN_SKIP 192
-#define WN_FIN_W 64
