@@ -149,7 +149,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     // 64-thread group, so items * replicas <= 64
     const int max_items = std::max(std::max(pl.NYm, pl.NXm), std::max(pl.NSm, std::max(pl.NAm, pl.NBm))) * BT;
     if (max_items > 64) return fail(WN_ERR_INVALID, "too many rows per block for this batch tile (use more blocks)");
-    if (nc <= 0) nc = 8;
+    if (nc <= 0) nc = 1;   // measured: scattered replica stores cost more than they save (profiles/r1_*)
     nc = std::min(nc, 64 / max_items);
     pl.ncopy = std::max(1, std::min(nc, P));
     pl.ex_yx = 0;
@@ -157,8 +157,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.ex_h1 = pl.ex_sk + pl.S;
     pl.ex_h2 = pl.ex_h1 + pl.S;
     pl.ex_elems = pl.ex_h2 + pl.O;
-    // replicas 4 KiB + 256 B apart so that they do not alias onto the same L2 slices
-    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + 511) / 512) * 512 + 32;
+    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + WN_XCHUNK - 1) / WN_XCHUNK + 1) * WN_XSTRIDE + 96;
 
     // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later
     ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);
@@ -185,7 +184,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_bar = take((long long)(2 * pl.nblobs + 8) * 8, 16);
         pl.sm_misc = take(16, 16);
         pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
-        pl.sm_ringtab = take((long long)ringtab.size() * 4 + 16, 16);
+        pl.sm_ringtab = take((long long)ringtab.size() / 2 * 3 * 4 + 16, 16);   // (offset, delay, position) per (layer, tap)
         pl.sm_xs = take(2LL * (pl.R + pl.G2) * BT * 4, 16);   // stash of (x, y), double buffered by stage parity
         const int nq1 = std::max(pl.NQ_A + pl.NQ_BO, std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
         pl.red1_floats = nq1 * 4 * BT * 4 + 4;                // partial sums of the 4 warps of a group

@@ -343,20 +343,26 @@ struct Engine {
     __device__ __forceinline__ bool check_abort(uint32_t what, long long& t0) {
         return wn_check_abort(s_abort, pp.err, pp.timeout_cycles, what, p, t0);
     }
+    // `relaxed` waits (anything off the critical path) back off with nanosleep so that they do not
+    // take issue slots and LSU bandwidth from the critical warp of the same SM sub-partition
+    template <bool relaxed = false>
     __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, uint32_t what) {
         uint32_t spins = 0;
         long long t0 = 0;
         while (!mbar_try_wait(bar, parity)) {
-            if (((++spins) & 255u) == 0 && check_abort(what, t0)) return false;
+            if (relaxed) __nanosleep(64);
+            if (((++spins) & (relaxed ? 63u : 255u)) == 0 && check_abort(what, t0)) return false;
         }
         return true;
     }
     // monotonic shared-memory counter (cross-group hand-off inside the block)
+    template <bool relaxed = false>
     __device__ __forceinline__ void wait_count(volatile int* cnt, int need, uint32_t what) {
         uint32_t spins = 0;
         long long t0 = 0;
         while (*cnt < need) {
-            if (((++spins) & 255u) == 0 && check_abort(what, t0)) {
+            if (relaxed) __nanosleep(32);
+            if (((++spins) & (relaxed ? 63u : 255u)) == 0 && check_abort(what, t0)) {
                 dead = true;
                 return;
             }
@@ -365,15 +371,16 @@ struct Engine {
     }
 
     // ---- wait for a broadcast vector: thread owns elements k = gt + j*WN_NTC.
+    // `src` is the base of the block's replica, `e0` the first element of the vector
     template <int E>
-    __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int K, uint32_t tag,
+    __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
                                                  float (&x)[E][BT]) {
         uint32_t bad = 0;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int k = gt + j * WN_NTC;
             if (k < K) {
-                const uint2* s = src + (size_t)k * BT;
+                const uint2* s = src + wn_pair_index((long long)(e0 + k) * BT);
                 if constexpr (BT == 1) {
                     const uint2 v = ld_pair(s);
                     x[j][0] = __uint_as_float(v.x);
@@ -396,10 +403,11 @@ struct Engine {
         return bad;
     }
     template <int E>
-    __device__ __forceinline__ void poll_vec(const uint2* __restrict__ src, int K, uint32_t tag, float (&x)[E][BT]) {
+    __device__ __forceinline__ void poll_vec(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
+                                             float (&x)[E][BT]) {
         uint32_t spins = 0;
         long long t0 = 0;
-        while (load_vec<E>(src, K, tag, x) != 0) {
+        while (load_vec<E>(src, e0, K, tag, x) != 0) {
             if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                 dead = true;
                 return;
@@ -408,13 +416,12 @@ struct Engine {
     }
     // two vectors of the same exchange (y then x): all loads of an attempt are in flight together
     template <int EA, int EB>
-    __device__ __forceinline__ void poll_vec2(const uint2* __restrict__ srca, int KA, float (&a)[EA][BT],
-                                              const uint2* __restrict__ srcb, int KB, float (&b)[EB][BT],
-                                              uint32_t tag) {
+    __device__ __forceinline__ void poll_vec2(const uint2* __restrict__ src, int ea, int KA, float (&a)[EA][BT],
+                                              int eb, int KB, float (&b)[EB][BT], uint32_t tag) {
         uint32_t spins = 0;
         long long t0 = 0;
         while (true) {
-            const uint32_t bad = load_vec<EA>(srca, KA, tag, a) | load_vec<EB>(srcb, KB, tag, b);
+            const uint32_t bad = load_vec<EA>(src, ea, KA, tag, a) | load_vec<EB>(src, eb, KB, tag, b);
             if (bad == 0) return;
             if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                 dead = true;
@@ -489,25 +496,30 @@ struct Engine {
         }
     }
     __device__ __forceinline__ void publish(int elem, int b, int copy, float v, uint32_t tag) {
-        st_pair(pp.xbuf + (size_t)copy * pl.copy_stride_pairs + ((size_t)elem * BT + b), v, tag);
+        st_pair(pp.xbuf + (size_t)copy * pl.copy_stride_pairs + wn_pair_index((long long)elem * BT + b), v, tag);
     }
 
-    // ---- weight slots
+    // ---- weight slots.  Every compute warp walks the blobs 0..L of every step in order; the ones that
+    // stream go through the ring, tracked by a running (slot, parity) pair (no divisions).
+    int rs_slot = 0;
+    uint32_t rs_par = 0;
     __device__ __forceinline__ const float* acquire_blob(int t, int i) {
         if (i < pl.nres) {
             if (t == 0 && !wait_bar(&bar_full[i], 0, 0x80000000u | (uint32_t)i)) dead = true;
             return slots + (size_t)i * pl.slot_floats;
         }
-        const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
-        const int slot = pl.nres + (int)(js % (uint32_t)pl.nring);
-        if (!wait_bar(&bar_full[slot], (js / (uint32_t)pl.nring) & 1u, 0x80000000u | (uint32_t)i)) dead = true;
+        const int slot = pl.nres + rs_slot;
+        if (!wait_bar(&bar_full[slot], rs_par, 0x80000000u | (uint32_t)i)) dead = true;
         return slots + (size_t)slot * pl.slot_floats;
     }
     __device__ __forceinline__ void release_blob(int t, int i) {
         if (i >= pl.nres) {
-            const uint32_t js = (uint32_t)t * (uint32_t)(pl.nblobs - pl.nres) + (uint32_t)(i - pl.nres);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[js % (uint32_t)pl.nring]);
+            if (lane == 0) mbar_arrive(&bar_empty[rs_slot]);
+            if (++rs_slot == pl.nring) {
+                rs_slot = 0;
+                rs_par ^= 1u;
+            }
         }
     }
 
@@ -529,7 +541,7 @@ struct Engine {
         for (uint32_t js = 0; js < total; ++js) {
             const uint32_t s = js % (uint32_t)pl.nring, u = js / (uint32_t)pl.nring;
             if (u > 0) {
-                if (!wait_bar(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
+                if (!wait_bar<true>(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
             }
             const uint32_t bytes = (uint32_t)wn_blob_floats(pl, i) * 4u;
             uint64_t* fb = &bar_full[pl.nres + s];
@@ -551,7 +563,7 @@ struct Engine {
         for (int t = 0; t < T; ++t) {
             const int par = t & 1, u = t >> 1;
             if (u > 0) {
-                if (!wait_bar(&bar_cempty[par], (u - 1) & 1u, 0x20000000u)) return;
+                if (!wait_bar<true>(&bar_cempty[par], (u - 1) & 1u, 0x20000000u)) return;
             }
             float ct[BT][WN_MAX_CI];
 #pragma unroll
@@ -807,8 +819,8 @@ struct Engine {
             pre_b += cd[rb * BT + fb];
         }
         for (int k = 0; k < kw - 1; ++k) {
-            const int off = ringtab[(l * (kw - 1) + k) * 2], D = ringtab[(l * (kw - 1) + k) * 2 + 1];
-            const volatile float* rp = ring + ((size_t)off + (uint32_t)t % (uint32_t)D) * RA4 * BT;
+            const int e = (l * (kw - 1) + k) * 3;
+            const volatile float* rp = ring + ((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT;   // offset + (t mod delay)
             pre_a += rp[ra * BT + fb];
             pre_b += rp[rb * BT + fb];
         }
@@ -890,10 +902,10 @@ struct Engine {
                     if (it_y >= 0) gate_pre(t, s, it_y / BT, it_y % BT, pre_a, pre_b);
                     WN_TICK(4);
                     {
-                        const uint2* src = xin + (size_t)(pl.ex_yx + (s - 1) * YX) * BT;
+                        const int e0 = pl.ex_yx + (s - 1) * YX;
                         const uint32_t tag = tagbase + wn_eid_yx(s - 1);
-                        if (s >= 2) poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
-                        else poll_vec<EG>(src, G2, tag, yr);          // x_0 is already in registers
+                        if (s >= 2) poll_vec2<EG, ER>(xin, e0, G2, yr, e0 + G2, R, xr, tag);
+                        else poll_vec<EG>(xin, e0, G2, tag, yr);      // x_0 is already in registers
                     }
                     WN_TICK(0);
                     float* xst = xs + (size_t)(s & 1) * R * BT;
@@ -949,10 +961,10 @@ struct Engine {
                 // ------------------------------------------------------------ stage L: skip of the last layer
                 const float* H = acquire_blob(t, L);
                 {
-                    const uint2* src = xin + (size_t)(pl.ex_yx + (L - 1) * YX) * BT;
+                    const int e0 = pl.ex_yx + (L - 1) * YX;
                     const uint32_t tag = tagbase + wn_eid_yx(L - 1);
-                    if (L >= 2) poll_vec2<EG, ER>(src, G2, yr, src + (size_t)G2 * BT, R, xr, tag);
-                    else poll_vec<EG>(src, G2, tag, yr);
+                    if (L >= 2) poll_vec2<EG, ER>(xin, e0, G2, yr, e0 + G2, R, xr, tag);
+                    else poll_vec<EG>(xin, e0, G2, tag, yr);
                 }
                 WN_TICK(0);
                 stash<ER>(xs + (size_t)(L & 1) * R * BT, R, xr);
@@ -980,9 +992,8 @@ struct Engine {
                 // ---------------------------------------------------------------- head (wavenet.py:315-319)
                 float* r1a = red1 + (size_t)((L + 1) & 1) * pl.red1_floats;
                 if (na > 0) {
-                    const uint2* src = xin + (size_t)pl.ex_sk * BT;
                     WN_DISPATCH_E(ES, { float h[E][BT];
-                                        poll_vec<E>(src, S, tagbase + wn_eid_sk(pl), h);
+                                        poll_vec<E>(xin, pl.ex_sk, S, tagbase + wn_eid_sk(pl), h);
                                         gemv<E>(H + pl.tb_Ha, pl.NQ_HA, S, h, r1a); });
                 }
                 if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
@@ -991,9 +1002,8 @@ struct Engine {
                     publish(pl.ex_h1 + a0 + fr, fb, cp_a, fmaxf(red_sum(r1a, fr, fb) + H[pl.tb_Hab + fr], 0.f), tagbase + wn_eid_h1(pl));
                 }
                 if (nb > 0) {
-                    const uint2* src = xin + (size_t)pl.ex_h1 * BT;
                     WN_DISPATCH_E(ES, { float h[E][BT];
-                                        poll_vec<E>(src, S, tagbase + wn_eid_h1(pl), h);
+                                        poll_vec<E>(xin, pl.ex_h1, S, tagbase + wn_eid_h1(pl), h);
                                         gemv<E>(H + pl.tb_Hb, pl.NQ_HB, S, h, r1); });
                 }
                 if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
@@ -1003,9 +1013,8 @@ struct Engine {
                 }
                 release_blob(t, L);
                 {
-                    const uint2* src = xin + (size_t)pl.ex_h2 * BT;
                     WN_DISPATCH_E(EO, { float h[E][BT];
-                                        poll_vec<E>(src, O, tagbase + wn_eid_h2(pl), h);
+                                        poll_vec<E>(xin, pl.ex_h2, O, tagbase + wn_eid_h2(pl), h);
                                         stash<E>(hs, O, h); });
                 }
                 WN_TICK(5);
@@ -1039,6 +1048,11 @@ struct Engine {
             sample_utt(t, warp);
             if (t + 1 < T) fetch_noise(t + 1, warp);
         }
+        // advance the ring positions to (t+1) mod delay
+        for (int i = WN_NT - 1 - tid; i < pl.L * (pl.kw - 1); i += WN_NT) {
+            const int pos = ringtab[i * 3 + 2] + 1;
+            ringtab[i * 3 + 2] = (pos == ringtab[i * 3 + 1]) ? 0 : pos;
+        }
     }
 
     // --------------------------------------------------------------------------------------
@@ -1060,7 +1074,7 @@ struct Engine {
         // one deferred stage: `Td` = older taps of `layer` (uses x), `Sk`/`skb` = skip rows of `layer`
         // (uses y; nullptr in the tail stage, where the critical group evaluates them itself)
         auto stage = [&](int t, int s, int layer, const float* Td, const float* Sk, const float* skb) {
-            wait_count(s_stash_cnt, nstash + 1, 0x04000000u);
+            wait_count<true>(s_stash_cnt, nstash + 1, 0x04000000u);
             ++nstash;
             WN_TICK(0);
             unstash<ER>(xs + (size_t)(s & 1) * R * BT, R, xr);
@@ -1087,8 +1101,8 @@ struct Engine {
                 // older-tap products of `layer` -> history ring (consumed at steps t+d, t+2d, conv.py:32-44)
                 for (int f = gt; f < nring_items; f += WN_NTC) {
                     const int dr = f / BT, db = f % BT, tap = dr / pl.RA, rr = dr % pl.RA;
-                    const int off = ringtab[(layer * (kw - 1) + tap) * 2], D = ringtab[(layer * (kw - 1) + tap) * 2 + 1];
-                    ring[((size_t)off + (uint32_t)t % (uint32_t)D) * pl.RA4 * BT + rr * BT + db] = red_sum(red, dr, db);
+                    const int e = (layer * (kw - 1) + tap) * 3;
+                    ring[((size_t)ringtab[e] + ringtab[e + 2]) * pl.RA4 * BT + rr * BT + db] = red_sum(red, dr, db);
                 }
                 // skip rows, accumulated in layer order (wavenet.py:312)
                 if (Sk) {
@@ -1160,7 +1174,11 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         for (size_t i = tid; i < n; i += WN_NTHREADS) eng.ring[i] = 0.f;
     }
     for (int i = tid; i < pl.NSm * BT + 4; i += WN_NTHREADS) eng.skipacc[i] = 0.f;
-    for (int i = tid; i < pl.L * (pl.kw - 1) * 2; i += WN_NTHREADS) eng.ringtab[i] = pp.ringtab[i];
+    for (int i = tid; i < pl.L * (pl.kw - 1); i += WN_NTHREADS) {
+        eng.ringtab[i * 3] = pp.ringtab[i * 2];           // offset of the ring (in positions)
+        eng.ringtab[i * 3 + 1] = pp.ringtab[i * 2 + 1];   // delay D
+        eng.ringtab[i * 3 + 2] = 0;                       // t mod D
+    }
     for (int k = tid; k < pl.R; k += WN_NTHREADS) {
         eng.first[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
         eng.first[pl.R + k] = pp.first_b[k];
