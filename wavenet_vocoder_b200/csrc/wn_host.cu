@@ -191,7 +191,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_red1 = take(2LL * pl.red1_floats * 4, 16);
         pl.red2_floats = (pl.NQ_D + pl.NQ_BS) * 4 * BT * 4 + 4;
         pl.sm_red2 = take(2LL * pl.red2_floats * 4, 16);      // two buffers each, alternating by stage
-        pl.sm_sb = take((long long)pl.L * pl.RA4 * BT * 4, 16);
+        pl.sm_sb = take(2LL * pl.L * pl.RA4 * BT * 4, 16);     // static part + per-step pre-sum table
         pl.sm_cond = take(pl.C > 0 ? 2LL * pl.L * pl.RA4 * BT * 4 : 16, 16);
         pl.sm_skipacc = take((long long)(pl.NSm * BT + 8 * pl.NQ_BS) * 4 + 16, 16);   // running skip sum + 2 bias stashes
         pl.sm_hs = take((long long)pl.O * BT * 4, 16);
@@ -217,7 +217,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.nring = 0;
     } else {
         if (fit < 2) return fail(WN_ERR_INVALID, "shared memory too small for two weight slots (use more blocks)");
-        int nr = c.ring_slots > 0 ? c.ring_slots : env_int("WN_RING_SLOTS", 3);
+        int nr = c.ring_slots > 0 ? c.ring_slots : env_int("WN_RING_SLOTS", 4);
         nr = (int)std::max<long long>(2, std::min<long long>(nr, fit));
         pl.nring = nr;
         pl.nres = (int)fit - nr;

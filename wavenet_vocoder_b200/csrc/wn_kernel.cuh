@@ -284,6 +284,7 @@ __device__ __noinline__ bool wn_check_abort(volatile int* s_abort, int* err, lon
 template <int BT, int ER, int EG>
 struct Engine {
     static constexpr int NV = 4 * BT;
+    static constexpr int NA = (BT >= 8) ? 1 : 2;     // quads reduced together (their shuffle chains overlap)
     const WnPlan& pl;
     const WnPtrs& pp;
     unsigned char* sm;
@@ -294,7 +295,7 @@ struct Engine {
     volatile int* s_stash_cnt;     // stashes published by the critical group (monotonic)
     volatile int* s_ddone_cnt;     // deferred-group warps finished, summed over stages (monotonic)
     int* ringtab;
-    float *xs, *ys, *red1, *red2, *sb, *cond, *skipacc, *hs, *noise, *first, *slots;
+    float *xs, *ys, *red1, *red2, *sb, *pre, *cond, *skipacc, *hs, *noise, *first, *slots;
     volatile float* ring;
     float* s_in;     // [BT] scalar feedback
     int* s_idx;      // [BT] class feedback
@@ -326,6 +327,7 @@ struct Engine {
         red1 = reinterpret_cast<float*>(sm + pl.sm_red1);
         red2 = reinterpret_cast<float*>(sm + pl.sm_red2);
         sb = reinterpret_cast<float*>(sm + pl.sm_sb);
+        pre = sb + (size_t)pl.L * pl.RA4 * BT;
         cond = reinterpret_cast<float*>(sm + pl.sm_cond);
         skipacc = reinterpret_cast<float*>(sm + pl.sm_skipacc);
         hs = reinterpret_cast<float*>(sm + pl.sm_hs);
@@ -484,15 +486,18 @@ struct Engine {
     template <int E>
     __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K, const float (&x)[E][BT],
                                          float* __restrict__ red, int q0 = 0) {
-        for (int q = 0; q < NQ; q += 2) {
-            float acc[2][NV];
+        for (int q = 0; q < NQ; q += NA) {
+            float acc[NA][NV];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
-            quad_fma<E>(w + (size_t)q * K * 4, K, x, acc[0]);
-            if (q + 1 < NQ) quad_fma<E>(w + (size_t)(q + 1) * K * 4, K, x, acc[1]);
-            reduce_scatter_multi<2, NV>(acc, lane);
-            quad_store(acc[0], q0 + q, red);
-            if (q + 1 < NQ) quad_store(acc[1], q0 + q + 1, red);
+            for (int h = 0; h < NA; ++h) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
+                if (q + h < NQ) quad_fma<E>(w + (size_t)(q + h) * K * 4, K, x, acc[h]);
+            }
+            reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+            for (int h = 0; h < NA; ++h)
+                if (q + h < NQ) quad_store(acc[h], q0 + q + h, red);
         }
     }
     __device__ __forceinline__ void publish(int elem, int b, int copy, float v, uint32_t tag) {
@@ -808,21 +813,40 @@ struct Engine {
             }
         }
     }
-    // everything of z_l that does not depend on this stage's broadcast, for gate pair `fr`
-    __device__ __forceinline__ void gate_pre(int t, int l, int fr, int fb, float& pre_a, float& pre_b) {
-        const int RA4 = pl.RA4, kw = pl.kw, ra = 2 * fr, rb = 2 * fr + 1;
-        pre_a = sb[((size_t)l * RA4 + ra) * BT + fb];
-        pre_b = sb[((size_t)l * RA4 + rb) * BT + fb];
+    // modules.py:154  tanh(a) * sigmoid(g) with a single division:
+    //   (1 - e^{-2a}) / ((1 + e^{-2a}) (1 + e^{-g}));  |a| is clamped where tanh has saturated in fp32.
+    // Absolute error ~1e-7 (the subtraction 1 - e^{-2a} loses relative, not absolute, accuracy near 0).
+    __device__ __forceinline__ static float gate(float a, float g) {
+        const float ac = fminf(fmaxf(a, -15.0f), 15.0f);
+        const float ea = expf(-2.0f * ac), eg = expf(-g);
+        return (1.0f - ea) / ((1.0f + ea) * (1.0f + eg));
+    }
+    // Everything of z_l(t) that does not depend on step t's broadcasts: (folded) bias + global conditioning
+    // + local conditioning projection + the queued products of the older taps.  The deferred group builds
+    // the whole table for step `t` while the critical group is still in the head of step t-1.
+    __device__ void build_pre(int t) {
+        const int L = pl.L, RA4 = pl.RA4, kw = pl.kw, n = L * pl.RA * BT;
         if (pl.C > 0) {
-            const float* cd = cond + ((size_t)(t & 1) * pl.L + l) * RA4 * BT;
-            pre_a += cd[ra * BT + fb];
-            pre_b += cd[rb * BT + fb];
+            if (!wait_bar<true>(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
         }
-        for (int k = 0; k < kw - 1; ++k) {
-            const int e = (l * (kw - 1) + k) * 3;
-            const volatile float* rp = ring + ((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT;   // offset + (t mod delay)
-            pre_a += rp[ra * BT + fb];
-            pre_b += rp[rb * BT + fb];
+        const float* cd = cond + (size_t)(t & 1) * L * RA4 * BT;
+        for (int i = gt; i < n; i += WN_NTC) {
+            const int b = i % BT, rr = (i / BT) % pl.RA, l = i / (BT * pl.RA);
+            const int idx = (l * RA4 + rr) * BT + b;
+            float v = sb[idx];
+            if (pl.C > 0) v += cd[idx];
+            for (int k = 0; k < kw - 1; ++k) {
+                const int e = (l * (kw - 1) + k) * 3;
+                int pos = ringtab[e + 2];
+                if (t > 0) { ++pos; if (pos == ringtab[e + 1]) pos = 0; }     // the table still holds (t-1) mod delay
+                v += ring[((size_t)ringtab[e] + pos) * RA4 * BT + rr * BT + b];
+            }
+            pre[idx] = v;
+        }
+        __syncwarp();
+        if (pl.C > 0) {
+            // the conditioning warp may refill cond[t&1] once all four deferred warps are done with it
+            if (lane == 0) mbar_arrive(&bar_cempty[t & 1]);
         }
     }
 
@@ -859,28 +883,27 @@ struct Engine {
         role(nb * BT, it_b, cp_b);
         if (!grpA) it_y = it_s = it_a = it_b = -1;
         if (grpA) it_x = -1;
+        const int pa_idx = it_y >= 0 ? (2 * (it_y / BT)) * BT + (it_y % BT) : 0;   // [row a_j][b]; row b_j is BT further
         float xr[ER][BT], yr[EG][BT];
         const bool prof = (pp.prof != nullptr) && tid == 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
 #define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
         int nstash = 0;      // stashes published so far == deferred stages started
         int ndone = 0;       // deferred stages this group has waited for
+        if (bar_or_n<3, WN_NT>(false)) return;      // the deferred group has built the pre-sums of step 0
 
         for (int t = 0; t < T; ++t) {
             const uint32_t tagbase = (uint32_t)t * NEID + 1u;
             if (prof) tc = clock64();
             bool step_dead = false;
             do {
-                if (pl.C > 0) {
-                    if (!wait_bar(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
-                }
                 make_x0(xr);
                 WN_TICK(7);
                 // ------------------------------------------------------------ stage 0: layer 0 from x_0
                 {
                     const float* W = acquire_blob(t, 0);
                     float pre_a = 0.f, pre_b = 0.f;
-                    if (it_y >= 0) gate_pre(t, 0, it_y / BT, it_y % BT, pre_a, pre_b);
+                    if (it_y >= 0) { pre_a = pre[pa_idx]; pre_b = pre[pa_idx + BT]; }
                     float* r1 = red1;                                   // partials buffers alternate by stage
                     gemv<ER>(W + pl.fb_Zx, NQ_A, R, xr, r1);
                     WN_TICK(1);
@@ -890,7 +913,7 @@ struct Engine {
                         const int fr = it_y / BT, fb = it_y % BT;
                         const float a = red_sum(r1, 2 * fr, fb) + pre_a;
                         const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
-                        publish(pl.ex_yx + y0 + fr, fb, cp_y, tanhf(a) * (1.0f / (1.0f + expf(-g))), tagbase + wn_eid_yx(0));
+                        publish(pl.ex_yx + y0 + fr, fb, cp_y, gate(a, g), tagbase + wn_eid_yx(0));
                     }
                     release_blob(t, 0);
                     WN_TICK(3);
@@ -899,7 +922,7 @@ struct Engine {
                 for (int s = 1; s < L; ++s) {
                     const float* W = acquire_blob(t, s);
                     float pre_a = 0.f, pre_b = 0.f;
-                    if (it_y >= 0) gate_pre(t, s, it_y / BT, it_y % BT, pre_a, pre_b);
+                    if (it_y >= 0) { pre_a = pre[pa_idx + s * pl.RA4 * BT]; pre_b = pre[pa_idx + s * pl.RA4 * BT + BT]; }
                     WN_TICK(4);
                     {
                         const int e0 = pl.ex_yx + (s - 1) * YX;
@@ -913,12 +936,12 @@ struct Engine {
                     stash<ER>(xst, R, xr);
                     stash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
                     // gate pre-activations of layer s (quads [0,NQ_A)) and residual rows x_s (quads [NQ_A,nqc))
-                    for (int q = 0; q < nqc; q += 2) {
-                        float acc[2][NV];
+                    for (int q = 0; q < nqc; q += NA) {
+                        float acc[NA][NV];
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+                        for (int h = 0; h < NA; ++h) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
+                            for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
                             const int qq = q + h;
                             if (qq < NQ_A) {
                                 quad_fma<EG>(W + pl.lb_Zy + (size_t)qq * G2 * 4, G2, yr, acc[h]);
@@ -927,9 +950,10 @@ struct Engine {
                                 quad_fma<EG>(W + pl.lb_Xo + (size_t)(qq - NQ_A) * G2 * 4, G2, yr, acc[h]);
                             }
                         }
-                        reduce_scatter_multi<2, NV>(acc, lane);
-                        quad_store(acc[0], q, r1);
-                        if (q + 1 < nqc) quad_store(acc[1], q + 1, r1);
+                        reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+                        for (int h = 0; h < NA; ++h)
+                            if (q + h < nqc) quad_store(acc[h], q + h, r1);
                     }
                     WN_TICK(1);
                     if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
@@ -944,7 +968,7 @@ struct Engine {
                         const int fr = it_y / BT, fb = it_y % BT;
                         const float a = red_sum(r1, 2 * fr, fb) + pre_a;
                         const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
-                        publish(pl.ex_yx + s * YX + y0 + fr, fb, cp_y, tanhf(a) * (1.0f / (1.0f + expf(-g))), tag);   // modules.py:154
+                        publish(pl.ex_yx + s * YX + y0 + fr, fb, cp_y, gate(a, g), tag);
                     }
                     if (it_x >= 0) {
                         // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
@@ -977,7 +1001,6 @@ struct Engine {
                     *s_stash_cnt = nstash + 1;
                 }
                 ++nstash;
-                if (pl.C > 0 && tid == 0) mbar_arrive(&bar_cempty[t & 1]);   // every gate of step t has read cond[t&1]
                 // skip rows of layers 0..L-2 were accumulated by the deferred group: wait for its stage L-1
                 if (L >= 2) { wait_count(s_ddone_cnt, WN_GW * (ndone + 1), 0x08000001u); ++ndone; }
                 WN_TICK(2);
@@ -1081,19 +1104,20 @@ struct Engine {
             if (Sk) unstash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
             float* red = red2 + (size_t)(s & 1) * pl.red2_floats;
             const int nq = Sk ? nqd : qoff;
-            for (int q = 0; q < nq; q += 2) {
-                float acc[2][NV];
+            for (int q = 0; q < nq; q += NA) {
+                float acc[NA][NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+                for (int h = 0; h < NA; ++h) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                    for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
                     const int qq = q + h;
                     if (qq < qoff) quad_fma<ER>(Td + (size_t)qq * R * 4, R, xr, acc[h]);
                     else if (qq < nq) quad_fma<EG>(Sk + (size_t)(qq - qoff) * G2 * 4, G2, yr, acc[h]);
                 }
-                reduce_scatter_multi<2, NV>(acc, lane);
-                quad_store(acc[0], q, red);
-                if (q + 1 < nq) quad_store(acc[1], q + 1, red);
+                reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+                for (int h = 0; h < NA; ++h)
+                    if (q + h < nq) quad_store(acc[h], q + h, red);
             }
             WN_TICK(1);
             const bool d = bar_or_n<2, WN_NTC>(dead);
@@ -1120,6 +1144,8 @@ struct Engine {
             return d;
         };
 
+        build_pre(0);
+        if (bar_or_n<3, WN_NT>(dead)) return;
         for (int t = 0; t < T; ++t) {
             if (prof) tc = clock64();
             bool step_dead = false;
@@ -1133,6 +1159,11 @@ struct Engine {
                 const float* H = acquire_blob(t, L);
                 step_dead = stage(t, L, L - 1, H + pl.tb_Td, nullptr, nullptr);
                 release_blob(t, L);
+            }
+            if (!step_dead && t + 1 < T) {
+                // all rings of step t are written (group barrier inside stage()): pre-sums of step t+1
+                if (bar_or_n<2, WN_NTC>(dead)) step_dead = true;
+                else build_pre(t + 1);
             }
             if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
             step_tail(t);
@@ -1161,7 +1192,7 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         for (int i = 0; i < pl.nring; ++i) mbar_init(&eng.bar_empty[i], WN_NWARP);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&eng.bar_cfull[i], 1);
-            mbar_init(&eng.bar_cempty[i], 1);
+            mbar_init(&eng.bar_cempty[i], WN_GW);
         }
         *eng.s_abort = 0;
         *eng.s_stash_cnt = 0;
