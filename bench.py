@@ -120,6 +120,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(T, U):
+    """DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of the same workload (profiles/r1_ncu_summary.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+            d = json.load(f)
+        if d.get("T") == T and d.get("utts_per_gpu") == U:
+            return d["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -269,7 +282,7 @@ def main():
                     "T": T_up, "api": "WaveNet.incremental_forward(c=host mel) -> .cpu()", "clocks": e["clocks"]},
             "gpu_launches": d["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(T, U), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": T * plan["weight_bytes_per_step"],
                          "flops_per_sample": plan["flops_per_sample"],
                          "fp32_tflops_achieved": sps * plan["flops_per_sample"] / 1e12},

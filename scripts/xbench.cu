@@ -29,23 +29,23 @@ __device__ __forceinline__ void spin(long long cycles) {
 // mode 1: warp 0 polls everything with 16-byte loads, hands over through shared memory
 // mode 2: warps 0-1 poll (half each), 16-byte loads
 // mode 3: like 0 but with 16-byte loads (each thread owns 2 adjacent elements)
+__device__ __forceinline__ long long pidx(long long lin, int xc, int xs) { return xc ? (lin / xc) * xs + (lin % xc) : lin; }
 __global__ void __launch_bounds__(256, 1)
-xbench(uint2* buf, int K, int nslots, int rounds, int mode, int crit_delay, int def_delay, long long* out, int ncopy,
-       long long copy_stride) {
+xbench(uint2* buf, int K, int nslots, int rounds, int mode, int crit_delay, int def_delay, long long* out, int xc,
+       long long xs_) {
     __shared__ float sh[2048];
     __shared__ int flag;
     const int tid = threadIdx.x, p = blockIdx.x, P = gridDim.x;
     const int per = K / P, k0 = p * per;
-    const uint2* rd = buf + (size_t)(p % ncopy) * copy_stride;
+    const int xs = (int)xs_;
     uint32_t acc = 1;
     __syncthreads();
     const long long t_start = clock64();
     for (int r = 0; r < rounds; ++r) {
         const uint32_t tag = (uint32_t)r + 1u;
-        uint2* slotw = buf + (size_t)(r % nslots) * K;
-        const uint2* slot = rd + (size_t)(r % nslots) * K;
+        const long long sbase = (long long)(r % nslots) * K;
         spin(crit_delay);
-        if (tid < per) for (int c = 0; c < ncopy; ++c) st_pair(slotw + (size_t)c * copy_stride + k0 + tid, acc + tid, tag);
+        if (tid < per) st_pair(buf + pidx(sbase + k0 + tid, xc, xs), acc + tid, tag);
         spin(def_delay);
         uint32_t sum = 0;
         const long long tw = clock64();
@@ -53,14 +53,14 @@ xbench(uint2* buf, int K, int nslots, int rounds, int mode, int crit_delay, int 
             while (true) {
                 WATCHDOG(tw)
                 uint32_t bad = 0; sum = 0;
-                for (int k = tid; k < K; k += 256) { const uint2 v = ld_pair(slot + k); bad |= v.y ^ tag; sum += v.x; }
+                for (int k = tid; k < K; k += 256) { const uint2 v = ld_pair(buf + pidx(sbase + k, xc, xs)); bad |= v.y ^ tag; sum += v.x; }
                 if (!bad) break;
             }
         } else if (mode == 3) {
             while (true) {
                 WATCHDOG(tw)
                 uint32_t bad = 0; sum = 0;
-                for (int k = 2 * tid; k < K; k += 512) { const uint4 v = ld_pair2(slot + k); bad |= (v.y ^ tag) | (v.w ^ tag); sum += v.x + v.z; }
+                for (int k = 2 * tid; k < K; k += 512) { const uint4 v = ld_pair2(buf + pidx(sbase + k, xc, xs)); bad |= (v.y ^ tag) | (v.w ^ tag); sum += v.x + v.z; }
                 if (!bad) break;
             }
         } else {
@@ -70,7 +70,7 @@ xbench(uint2* buf, int K, int nslots, int rounds, int mode, int crit_delay, int 
                     WATCHDOG(tw)
                     uint32_t bad = 0;
                     for (int k = 2 * tid; k < K; k += 64 * nw) {
-                        const uint4 v = ld_pair2(slot + k);
+                        const uint4 v = ld_pair2(buf + pidx(sbase + k, xc, xs));
                         bad |= (v.y ^ tag) | (v.w ^ tag);
                         sh[k] = __uint_as_float(v.x); sh[k + 1] = __uint_as_float(v.z);
                     }
@@ -110,7 +110,7 @@ int main(int argc, char** argv) {
     setvbuf(stdout, NULL, _IONBF, 0);
     const int rounds = 4000, nslots = 27;
     uint2* buf; long long* out;
-    const size_t nb = (size_t)8 * 64 * 1024 * sizeof(uint2);
+    const size_t nb = (size_t)64 * 64 * 1024 * sizeof(uint2);
     cudaMalloc(&buf, nb); cudaMalloc(&out, 256 * sizeof(long long));
     int dev = 0, clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev);
     long long h[256];
@@ -125,30 +125,26 @@ int main(int argc, char** argv) {
         chase<<<1, 1>>>(buf, 4000, out); cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost);
         printf("dependent ld.relaxed.gpu chain: %.0f cycles/load\n", (double)h[0] / 4000);
     }
-    const int Ps[] = {32, 128};
-    const int Ks[] = {256, 768};
+    const int lay[][2] = {{0, 0}, {32, 544}, {16, 272}, {16, 1040}, {4, 516}, {32, 2080}, {1, 33}};
     const int delays[][2] = {{0, 0}, {500, 1500}};
     for (int di = 0; di < 2; ++di)
-        for (int K : Ks)
-            for (int P : Ps)
-                for (int mode = 0; mode < 4; ++mode)
-                    for (int ncopy : {1, 4}) {
-                        if (ncopy > 1 && (mode != 0 || di != 0)) continue;
-                        cudaMemset(buf, 0, nb);
-                        void* args[] = {&buf, (void*)&K, (void*)&nslots, (void*)&rounds, &mode, (void*)&delays[di][0],
-                                        (void*)&delays[di][1], &out, &ncopy, nullptr};
-                        long long stride = 64 * 1024; args[9] = &stride;
-                        cudaError_t e = cudaLaunchCooperativeKernel((void*)xbench, dim3(P), dim3(256), args, 0, 0);
-                        cudaDeviceSynchronize();
-                        cudaError_t e2 = cudaGetLastError();
-                        if (e != cudaSuccess || e2 != cudaSuccess) { printf("launch failed %s %s\n", cudaGetErrorString(e), cudaGetErrorString(e2)); return 1; }
-                        cudaMemcpy(h, out, P * sizeof(long long), cudaMemcpyDeviceToHost);
-                        int ab = 0; cudaMemcpyFromSymbol(&ab, g_abort, sizeof(int));
-                        if (ab) { printf("WATCHDOG fired: K=%d P=%d mode=%d ncopy=%d\n", K, P, mode, ncopy); ab = 0; cudaMemcpyToSymbol(g_abort, &ab, sizeof(int)); continue; }
-                        long long mx = 0; for (int i = 0; i < P; ++i) mx = h[i] > mx ? h[i] : mx;
-                        printf("delay(%4d,%4d) K=%4d P=%3d mode=%d ncopy=%d : %7.0f cycles/round  (minus delays: %6.0f)\n",
-                               delays[di][0], delays[di][1], K, P, mode, ncopy, (double)mx / rounds,
-                               (double)mx / rounds - delays[di][0] - delays[di][1]);
-                    }
+        for (int K : {256, 768})
+            for (int P : {64, 128})
+                for (int li = 0; li < 7; ++li) {
+                    int mode = 0, xc = lay[li][0]; long long xs = lay[li][1];
+                    cudaMemset(buf, 0, nb);
+                    void* args[] = {&buf, (void*)&K, (void*)&nslots, (void*)&rounds, &mode, (void*)&delays[di][0],
+                                    (void*)&delays[di][1], &out, &xc, &xs};
+                    cudaError_t e = cudaLaunchCooperativeKernel((void*)xbench, dim3(P), dim3(256), args, 0, 0);
+                    cudaDeviceSynchronize();
+                    cudaError_t e2 = cudaGetLastError();
+                    if (e != cudaSuccess || e2 != cudaSuccess) { printf("launch failed %s %s\n", cudaGetErrorString(e), cudaGetErrorString(e2)); return 1; }
+                    cudaMemcpy(h, out, P * sizeof(long long), cudaMemcpyDeviceToHost);
+                    int ab = 0; cudaMemcpyFromSymbol(&ab, g_abort, sizeof(int));
+                    if (ab) { printf("WATCHDOG fired: K=%d P=%d layout=(%d,%lld)\n", K, P, xc, xs); ab = 0; cudaMemcpyToSymbol(g_abort, &ab, sizeof(int)); continue; }
+                    long long mx = 0; for (int i = 0; i < P; ++i) mx = h[i] > mx ? h[i] : mx;
+                    printf("delay(%4d,%4d) K=%4d P=%3d layout chunk=%2d stride=%4lld pairs : %7.0f cycles/round (minus delays %6.0f)\n",
+                           delays[di][0], delays[di][1], K, P, xc, xs, (double)mx / rounds, (double)mx / rounds - delays[di][0] - delays[di][1]);
+                }
     return 0;
 }

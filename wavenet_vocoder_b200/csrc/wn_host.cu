@@ -730,8 +730,11 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)a->stream;
-    for (int b0 = 0; b0 < a->B; b0 += WN_MAX_BT) {
-        const int Bc = std::min(WN_MAX_BT, a->B - b0);
+    // batch tiles: 8 utterances per launch spill registers in this build (168/thread with 10 warps), so
+    // the default tile is 4 (measured faster per utterance, profiles/r1_*sweep*); WN_MAX_TILE=8 overrides
+    const int tile = std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)));
+    for (int b0 = 0; b0 < a->B; b0 += tile) {
+        const int Bc = std::min(tile, a->B - b0);
         rc = launch_chunk(h, a, b0, Bc, st);
         if (rc) return rc;
     }
@@ -776,7 +779,7 @@ int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out) {
     if (!h || !out) return fail(WN_ERR_INVALID, "null argument");
     WnPlan pl;
     std::vector<int> rt;
-    int32_t rc = build_plan(h->cfg, std::min(batch, WN_MAX_BT), h->num_sms, h->smem_cap, pl, rt);
+    int32_t rc = build_plan(h->cfg, std::min(batch, std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)))), h->num_sms, h->smem_cap, pl, rt);
     if (rc) return rc;
     fill_info(h->cfg, pl, out);
     out->launches = h->launches;
