@@ -64,25 +64,34 @@ def oracle_parts(model):
     return orc, cfg, orc.weights_from_state_dict(cfg, sd)
 
 
-def time_cpu_port(model, n_samples, warm, threads):
-    """The reference algorithm on the host: samples/s over ``n_samples`` steps after ``warm``."""
+REF_THREADS = 4       # the reference pins torch.set_num_threads(4) for synthesis (synthesis.py:37)
+
+
+def time_cpu_port(model, n_samples, warm, threads, budget_s=25.0):
+    """The reference algorithm on the host: samples/s after ``warm`` samples.  The number of timed
+    samples is cut so that the run stays inside ``budget_s`` seconds (probed on the first samples)."""
     orc, cfg, w = oracle_parts(model)
     torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(1)
-    T = warm + n_samples
-    c = torch.randn(1, 80, T, generator=gen)
     marks = {}
 
-    def progress(it):
-        for t in it:
-            if t == warm:
-                marks["t0"] = time.perf_counter()
-            yield t
-    torch.manual_seed(0)
-    with torch.no_grad():
-        orc.incremental_forward(cfg, w, c=c, T=T, progress=progress)
-    dt = time.perf_counter() - marks["t0"]
-    return n_samples / dt, dt
+    def run(T, warm_):
+        c = torch.randn(1, 80, T, generator=gen)
+
+        def progress(it):
+            for t in it:
+                if t == warm_:
+                    marks["t0"] = time.perf_counter()
+                yield t
+        torch.manual_seed(0)
+        with torch.no_grad():
+            orc.incremental_forward(cfg, w, c=c, T=T, progress=progress)
+        return time.perf_counter() - marks["t0"]
+
+    probe = run(10 + 30, 10) / 30.0                      # seconds per sample
+    n = int(max(50, min(n_samples, budget_s / max(probe, 1e-6))))
+    dt = run(warm + n, warm)
+    return n / dt, dt, n
 
 
 class ClockSampler:
@@ -146,24 +155,27 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     model = build_model()
-    threads = os.cpu_count() or 1
-    n = args.ref_samples
+    threads = min(REF_THREADS, os.cpu_count() or 1)
     vals = []
+    per_step_budget = max(3.0, 120.0 / max(1, args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        v, dt = time_cpu_port(model, n, 20, threads)
+        v, dt, n = time_cpu_port(model, args.ref_samples, 20, threads, budget_s=per_step_budget)
         if i >= args.warmup:
-            vals.append((v, dt))
-    sps = sum(n for _ in vals) / sum(dt for _, dt in vals)
+            vals.append((v, dt, n))
+    n = vals[0][2]
+    sps = sum(x[2] for x in vals) / sum(x[1] for x in vals)
     line = {
         "impl": "reference", "metric": "audio samples/sec (22.05 kHz MoL, 24-layer)", "value": sps,
         "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals), "higher_is_better": True,
+        "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf": SAMPLE_RATE / sps,
         "config": {"workload": "BASELINE config 2: MoL-10 24L/4 stacks 512/512/256, 80-mel, B=1; "
                                "each step = %d samples of the same per-sample loop on the host CPU" % n},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "%d samples after 20 warm-up samples per step, torch CPU fp32, %d threads" % (n, threads)},
+                         "host_cpus": os.cpu_count(),
+                         "sample": "%d samples after 20 warm-up samples per step, torch CPU fp32, %d threads as the "
+                                   "reference ships (synthesis.py:37)" % (n, threads)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -288,12 +300,14 @@ def main():
                          "fp32_tflops_achieved": sps * plan["flops_per_sample"] / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            v, dt = time_cpu_port(model.cpu(), args.cpu_samples, 100, threads)
+            threads = min(REF_THREADS, os.cpu_count() or 1)
+            v, dt, n = time_cpu_port(model.cpu(), args.cpu_samples, 100, threads)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "host_cpus": os.cpu_count(),
                                     "sample": "%d samples after 100 warm-up samples of the same config-2 loop "
                                               "(oracle port of the reference CPU incremental_forward, torch fp32, "
-                                              "%d threads, %.1f s)" % (args.cpu_samples, threads, dt)}
+                                              "%d threads as the reference ships (synthesis.py:37), %.1f s)"
+                                              % (n, threads, dt)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
