@@ -9,6 +9,7 @@ of the reference (modules.py:112-163, conv.py:17-46) is NOT implemented here: it
 csrc/wn_kernel.cuh and is reached through ``WaveNet.incremental_forward``.
 """
 import math
+import warnings
 
 import torch
 from torch import nn
@@ -20,7 +21,9 @@ def _normed_conv1d(cin, cout, ksize, dilation=1, padding=0, bias=True):
     nn.init.kaiming_normal_(conv.weight, nonlinearity="relu")
     if conv.bias is not None:
         nn.init.constant_(conv.bias, 0)
-    return nn.utils.weight_norm(conv)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", FutureWarning)      # the old API keeps the reference's weight_g/weight_v keys
+        return nn.utils.weight_norm(conv)
 
 
 def Conv1d(in_channels, out_channels, kernel_size, dropout=0, **kwargs):

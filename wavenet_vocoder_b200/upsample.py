@@ -5,6 +5,8 @@ They run ONCE per utterance before the sample loop (reference wavenet.py:272-276
 the hot path (SURVEY.md 8(f-1) lists them as the next row); they stay plain PyTorch here and keep
 the reference's parameter names (upsample.py:29-85 there) so checkpoints load.
 """
+import warnings
+
 import numpy as np
 import torch
 from torch import nn
@@ -34,7 +36,9 @@ class UpsampleNetwork(nn.Module):
                              bias=False)
             conv.weight.data.fill_(1.0 / np.prod(ksize))
             self.up_layers.append(Stretch2d(s, 1, mode))
-            self.up_layers.append(nn.utils.weight_norm(conv))
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", FutureWarning)
+                self.up_layers.append(nn.utils.weight_norm(conv))
             if upsample_activation != "none":
                 self.up_layers.append(getattr(nn, upsample_activation)(**upsample_activation_params))
 
