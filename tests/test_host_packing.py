@@ -93,8 +93,8 @@ def test_plan_numbers_match_survey_table():
                        output_distribution="Logistic")
     p5 = plan_of(cfg5)
     assert p5["flops_per_sample"] == 34061824
-    for b in (1, 2, 4, 8):
-        assert plan_of(cfg, b)["batch_tile"] == b and plan_of(cfg, b)["smem_bytes"] <= SMEM
+    for b in (1, 2, 4, 8):          # larger batches run in tiles of 4 utterances per launch
+        assert plan_of(cfg, b)["batch_tile"] == min(b, 4) and plan_of(cfg, b)["smem_bytes"] <= SMEM
 
 
 def test_planner_rejects_bad_shapes():

@@ -19,7 +19,7 @@
 #endif
 #endif
 
-#define WN_NT 256                 // compute threads per block (8 warps)
+#define WN_NT 192                 // compute threads per block (6 warps: gate, residual, skip, 2x taps, 2nd gate)
 #define WN_NWARP (WN_NT / 32)
 #define WN_AUX_WARPS 2            // +1 weight-streaming (TMA) warp, +1 conditioning warp
 #define WN_NTHREADS (WN_NT + 32 * WN_AUX_WARPS)
