@@ -911,7 +911,7 @@ struct Engine {
             if (roleZ) {
                 const bool zwork = (warp == 0) || (zidx < NQ_A);
                 for (int s = 0; s < L && !dead; ++s) {
-                    if (!zwork) { release_blob(t, s); continue; }
+                    if (!zwork) { acquire_blob(t, s); release_blob(t, s); continue; }   // never run ahead of the ring
                     const float* W = acquire_blob(t, s);
                     const uint32_t tag_in = tagbase + wn_eid_yx(s - 1), tag_out = tagbase + wn_eid_yx(s);
                     const int e_in = pl.ex_yx + (s - 1) * YX;
@@ -981,12 +981,11 @@ struct Engine {
             }
             // ================================================================ residual warps
             if (roleX) {
+                acquire_blob(t, 0);
                 release_blob(t, 0);
                 for (int s = 1; s < L && !dead; ++s) {
-                    const float* W = nullptr;
-                    bool have = false;
+                    const float* W = acquire_blob(t, s);
                     for (int q = 0; q < NQ_BO; ++q) {
-                        if (!have) { W = acquire_blob(t, s); have = true; }
                         // x_s rows of this quad: conv1x1_out(y_{s-1}) + x_{s-1}  (modules.py:160-162)
                         const int r = my_row(), b = my_b(), row = 4 * q + r;
                         const bool fin = holds_value() && row < nx;
@@ -1025,6 +1024,7 @@ struct Engine {
             }
             // ================================================================ skip warp and older-tap warps
             if (roleS || roleT) {
+                acquire_blob(t, 0);
                 release_blob(t, 0);
                 for (int s = 1; s <= L && !dead; ++s) {
                     const bool tail = (s == L);
@@ -1121,6 +1121,7 @@ struct Engine {
                                     stash<E>(hs, O, h); });
                 WN_TICK(0);
             }
+            if (warp == 5) acquire_blob(t, L);
             release_blob(t, L);
             if (step_end(t, false)) return;
             WN_TICK(6);
