@@ -82,7 +82,7 @@ def test_make_generation_fast_gives_same_result():
     assert float((y1 - y2).abs().max()) <= 1e-5
 
 
-@pytest.mark.parametrize("P", [2, 3, 8, 32])
+@pytest.mark.parametrize("P", [4, 5, 8, 32])
 def test_any_block_count_gives_same_head_outputs(P):
     """The row partition must not change the result beyond fp32 reassociation."""
     from wavenet_vocoder_b200.engine import SynthesisEngine

@@ -123,12 +123,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ uint2 ld_pair(const uint2* p) {
     uint2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    // weak, L2-coherent (.cg bypasses L1): unlike ld.relaxed.gpu, several of these from one thread overlap.
+    // Data and tag share one 8-byte word, so no ordering between different loads is needed.
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint4 ld_pair2(const uint2* p) {
     uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p)
                  : "memory");
