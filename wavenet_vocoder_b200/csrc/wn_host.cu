@@ -119,8 +119,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.fb_zb = o; o += pl.RA4;
     pl.fb_floats = align_up(o, 4);
     o = 0;
-    pl.lb_Zy = o; o += pl.NQ_A * pl.G2 * 4;
-    pl.lb_Zx = o; o += pl.NQ_A * pl.R * 4;
+    pl.lb_Zy = o; pl.lb_Zx = o; o += pl.NQ_A * (pl.G2 + pl.R) * 4;
     pl.lb_Xo = o; o += pl.NQ_BO * pl.G2 * 4;
     pl.lb_Td = o; o += pl.NQ_D * pl.R * 4;
     pl.lb_Sk = o; o += pl.NQ_BS * pl.G2 * 4;
@@ -351,8 +350,8 @@ static void pack_cta(const WnPlan& pl, const wn_weights& w, const Folded& f, int
         const wn_layer_weights& pw = w.layers[s - 1];
         for (int rr = 0; rr < 2 * ny; ++rr) {
             const int g = grow(rr);
-            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Zy, G2, rr, k, f.M[s - 1][(size_t)g * G2 + k]);
-            for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Zx, R, rr, k, f.V[s][(size_t)g * R + k]);
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Zy, G2 + R, rr, k, f.M[s - 1][(size_t)g * G2 + k]);
+            for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Zy, G2 + R, rr, G2 + k, f.V[s][(size_t)g * R + k]);
             blob[pl.lb_zb + rr] = f.zb[s][g];
         }
         for (int r = 0; r < nx; ++r) {

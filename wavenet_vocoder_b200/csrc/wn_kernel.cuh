@@ -372,36 +372,29 @@ struct Engine {
         __threadfence_block();
     }
 
-    // ---- wait for a broadcast vector: thread owns elements k = gt + j*WN_NTC.
+    // ---- wait for a broadcast vector with the 128 threads of warps 0-3: thread owns k = gt + j*128
     // `src` is the base of the block's replica, `e0` the first element of the vector
     template <int E>
     __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
                                                  float (&x)[E][BT]) {
         uint32_t bad = 0;
+        uint2 raw[E][BT];
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const int k = gt + j * WN_NTC;
-            if (k < K) {
-                const uint2* s = src + wn_pair_index((long long)(e0 + k) * BT);
-                if constexpr (BT == 1) {
-                    const uint2 v = ld_pair(s);
-                    x[j][0] = __uint_as_float(v.x);
-                    bad |= v.y ^ tag;
-                } else {
 #pragma unroll
-                    for (int b = 0; b < BT; b += 2) {
-                        const uint4 v = ld_pair2(s + b);
-                        x[j][b] = __uint_as_float(v.x);
-                        bad |= v.y ^ tag;
-                        x[j][b + 1] = __uint_as_float(v.z);
-                        bad |= v.w ^ tag;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+            for (int b = 0; b < BT; ++b) {
+                raw[j][b] = make_uint2(0u, tag);
+                if (k < K) raw[j][b] = ld_pair(src + wn_pair_index((long long)(e0 + k) * BT + b));
             }
         }
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+                bad |= raw[j][b].y ^ tag;
+                x[j][b] = __uint_as_float(raw[j][b].x);
+            }
         return bad;
     }
     template <int E>
@@ -716,27 +709,44 @@ struct Engine {
         return K <= WN_NTC ? 1 : (K <= 2 * WN_NTC ? 2 : (K <= 4 * WN_NTC ? 4 : 8));
     }
 
-    // one attempt to read K elements starting at element e0 (lane owns e = lane + 32 j)
+    // one attempt to read K elements starting at element e0 (lane owns e = lane + 32 j).  ALL loads are
+    // issued before any result is looked at: ptxas otherwise interleaves each few loads with the tag
+    // checks that consume them and the warp pays one L2 round trip per group instead of one in total.
     __device__ __forceinline__ uint32_t wload(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
                                               float (&v)[EK][BT]) {
         uint32_t bad = 0;
+        if constexpr (BT == 1) {
+            uint2 raw[EK];
 #pragma unroll
-        for (int j = 0; j < EK; ++j) {
-            const int e = lane + 32 * j;
-            if (e < K) {
-                const uint2* sp = src + wn_pair_index((long long)(e0 + e) * BT);
-                if constexpr (BT == 1) {
-                    const uint2 w = ld_pair(sp);
-                    v[j][0] = __uint_as_float(w.x);
-                    bad |= w.y ^ tag;
-                } else {
+            for (int j = 0; j < EK; ++j) {
+                const int e = lane + 32 * j;
+                raw[j] = make_uint2(0u, tag);
+                if (e < K) raw[j] = ld_pair(src + wn_pair_index((long long)(e0 + e)));
+            }
 #pragma unroll
-                    for (int b = 0; b < BT; b += 2) {
-                        const uint4 w = ld_pair2(sp + b);
-                        v[j][b] = __uint_as_float(w.x);
-                        bad |= w.y ^ tag;
-                        v[j][b + 1] = __uint_as_float(w.z);
-                        bad |= w.w ^ tag;
+            for (int j = 0; j < EK; ++j) {
+                bad |= raw[j].y ^ tag;
+                if (lane + 32 * j < K) v[j][0] = __uint_as_float(raw[j].x);
+            }
+        } else {
+            uint4 raw[EK][BT / 2];
+#pragma unroll
+            for (int j = 0; j < EK; ++j) {
+                const int e = lane + 32 * j;
+#pragma unroll
+                for (int b = 0; b < BT / 2; ++b) {
+                    raw[j][b] = make_uint4(0u, tag, 0u, tag);
+                    if (e < K) raw[j][b] = ld_pair2(src + wn_pair_index((long long)(e0 + e) * BT) + 2 * b);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < EK; ++j) {
+#pragma unroll
+                for (int b = 0; b < BT / 2; ++b) {
+                    bad |= (raw[j][b].y ^ tag) | (raw[j][b].w ^ tag);
+                    if (lane + 32 * j < K) {
+                        v[j][2 * b] = __uint_as_float(raw[j][b].x);
+                        v[j][2 * b + 1] = __uint_as_float(raw[j][b].z);
                     }
                 }
             }
@@ -927,10 +937,7 @@ struct Engine {
 #pragma unroll
                         for (int i = 0; i < NV; ++i) acc[i] = 0.f;
                         if (s == 0) wfma(W + pl.fb_Zx + (size_t)q * R * 4, G2, R, v, acc);
-                        else {
-                            wfma(W + pl.lb_Zy + (size_t)q * G2 * 4, 0, G2, v, acc);
-                            wfma(W + pl.lb_Zx + (size_t)q * R * 4, G2, R, v, acc);
-                        }
+                        else wfma(W + pl.lb_Zy + (size_t)q * YX * 4, 0, YX, v, acc);     // [M_{s-1} | V_s] rows over (y ; x)
                         reduce_scatter<NV>(acc, lane);
                         // rows of the quad are a_j, b_j, a_{j+1}, b_{j+1}: the b row sits BT values (8 lanes) further
                         const float other = __shfl_down_sync(0xffffffffu, acc[0], BT * LPV);

@@ -47,8 +47,8 @@ struct WnPlan {
     // first blob (stage 0): current tap of layer 0 + bias
     int fb_Zx, fb_zb, fb_floats;
     // layer blob (stage s = 1..L-1)
-    int lb_Zy;      // M_{s-1} rows          [NQ_A][G2][4]
-    int lb_Zx;      // V_s rows              [NQ_A][R][4]
+    int lb_Zy;      // [M_{s-1} | V_s] rows over the concatenated input (y ; x)   [NQ_A][G2+R][4]
+    int lb_Zx;      // (= lb_Zy, kept for tooling)
     int lb_Xo;      // conv1x1_out_{s-1} rows [NQ_BO][G2][4]  (the residual stream itself, published as x_s)
     int lb_Td;      // older taps of layer s-1 [NQ_D][R][4]   (deferred: queued for steps t+d, t+2d ...)
     int lb_Sk;      // conv1x1_skip_{s-1} rows [NQ_BS][G2][4] (deferred)
