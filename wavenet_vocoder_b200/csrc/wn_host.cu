@@ -149,12 +149,17 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     if (pl.NQ_BS > 2) return fail(WN_ERR_INVALID, "more than 8 skip rows per block (use more blocks)");
     (void)nc;
     pl.ncopy = 1;          // measured: scattered replica stores cost more than they save (profiles/r1_*)
+    if ((pl.G2 & 1) || (pl.R & 1) || (pl.S & 1))
+        return fail(WN_ERR_INVALID, "residual, gate/2 and skip channel counts must be even (16-byte bulk copies)");
+    if (pl.S > pl.G2 + pl.R) return fail(WN_ERR_INVALID, "skip_channels > residual + gate/2 is not supported");
     pl.ex_yx = 0;
     pl.ex_sk = pl.L * (pl.G2 + pl.R);
     pl.ex_h1 = pl.ex_sk + pl.S;
     pl.ex_h2 = pl.ex_h1 + pl.S;
-    pl.ex_elems = pl.ex_h2 + pl.O;
-    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + WN_XCHUNK - 1) / WN_XCHUNK + 1) * WN_XSTRIDE + 96;
+    pl.ex_elems = pl.ex_h2 + pl.O + (pl.O & 1);
+    pl.land_z_pairs = (pl.G2 + pl.R) * BT + 2;
+    pl.land_y_pairs = std::max(pl.G2, pl.S) * BT + 2;
+    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + 63) / 64) * 64 + 64;
 
     // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later
     ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);
@@ -195,6 +200,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_noise = take((long long)BT * (pl.O + 2) * 4, 16);
         pl.sm_first = take(2LL * pl.R * 4, 16);
         pl.sm_ring = take(ring_smem ? ring_bytes : 16, 16);
+        pl.sm_land = take((2LL * pl.land_z_pairs + 2LL * pl.land_y_pairs) * 8 + 64, 128);   // TMA landing buffers + 4 mbarriers
         pl.sm_slots = take(0, 128);
         return off;
     };

@@ -709,64 +709,49 @@ struct Engine {
         return K <= WN_NTC ? 1 : (K <= 2 * WN_NTC ? 2 : (K <= 4 * WN_NTC ? 4 : 8));
     }
 
-    // one attempt to read K elements starting at element e0 (lane owns e = lane + 32 j).  ALL loads are
-    // issued before any result is looked at: ptxas otherwise interleaves each few loads with the tag
-    // checks that consume them and the warp pays one L2 round trip per group instead of one in total.
-    __device__ __forceinline__ uint32_t wload(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
-                                              float (&v)[EK][BT]) {
-        uint32_t bad = 0;
-        if constexpr (BT == 1) {
-            uint2 raw[EK];
-#pragma unroll
-            for (int j = 0; j < EK; ++j) {
-                const int e = lane + 32 * j;
-                raw[j] = make_uint2(0u, tag);
-                if (e < K) raw[j] = ld_pair(src + wn_pair_index((long long)(e0 + e)));
-            }
-#pragma unroll
-            for (int j = 0; j < EK; ++j) {
-                bad |= raw[j].y ^ tag;
-                if (lane + 32 * j < K) v[j][0] = __uint_as_float(raw[j].x);
-            }
-        } else {
-            uint4 raw[EK][BT / 2];
-#pragma unroll
-            for (int j = 0; j < EK; ++j) {
-                const int e = lane + 32 * j;
-#pragma unroll
-                for (int b = 0; b < BT / 2; ++b) {
-                    raw[j][b] = make_uint4(0u, tag, 0u, tag);
-                    if (e < K) raw[j][b] = ld_pair2(src + wn_pair_index((long long)(e0 + e) * BT) + 2 * b);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < EK; ++j) {
-#pragma unroll
-                for (int b = 0; b < BT / 2; ++b) {
-                    bad |= (raw[j][b].y ^ tag) | (raw[j][b].w ^ tag);
-                    if (lane + 32 * j < K) {
-                        v[j][2 * b] = __uint_as_float(raw[j][b].x);
-                        v[j][2 * b + 1] = __uint_as_float(raw[j][b].z);
-                    }
-                }
-            }
-        }
-        return bad;
-    }
-    // wait for the vector; `xe` >= 0 additionally fetches one element (for all b) into `xv`
-    __device__ __forceinline__ void wpoll(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
-                                          float (&v)[EK][BT], int xe = -1, int xb = 0, float* xv = nullptr) {
+    // Wait for a broadcast vector: ONE TMA bulk copy (cp.async.bulk, reads through L2 and never L1, fully
+    // pipelined by the copy engine) lands the K*BT pairs in a warp-private shared-memory buffer; the lanes
+    // then check the tags there and the copy is re-issued until every pair carries this exchange's tag.
+    // (L1-bypassing loads issued by the warp itself cost ~250 cycles EACH, profiles/r1_*: 24 per lane = 6000.)
+    // `xe` >= 0 additionally fetches one element (for utterance xb) into `xv` with an ordinary coherent load.
+    __device__ __forceinline__ void tpoll(uint2* land, uint64_t* bar, uint32_t& ph, const uint2* __restrict__ src,
+                                          int e0, int K, uint32_t tag, float (&v)[EK][BT], int xe = -1, int xb = 0,
+                                          float* xv = nullptr) {
         uint32_t spins = 0;
         long long t0 = 0;
+        const uint32_t bytes = ((uint32_t)(K * BT) * 8u + 15u) & ~15u;
         while (true) {
-            uint32_t bad = wload(src, e0, K, tag, v);
+            if (lane == 0) {
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(land, src + (size_t)e0 * BT, bytes, bar);
+            }
+            uint32_t bad = 0;
             if (xe >= 0) {
-                const uint2 w = ld_pair(src + wn_pair_index((long long)xe * BT + xb));
+                const uint2 w = ld_pair(src + ((size_t)xe * BT + xb));
                 *xv = __uint_as_float(w.x);
                 bad |= w.y ^ tag;
             }
+            while (!mbar_try_wait(bar, ph)) {
+                if (((++spins) & 255u) == 0 && check_abort(tag, t0)) {
+                    dead = true;
+                    return;
+                }
+            }
+            ph ^= 1u;
+#pragma unroll
+            for (int j = 0; j < EK; ++j) {
+                const int e = lane + 32 * j;
+                if (e < K) {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) {
+                        const uint2 w = land[e * BT + b];
+                        v[j][b] = __uint_as_float(w.x);
+                        bad |= w.y ^ tag;
+                    }
+                }
+            }
             if (__all_sync(0xffffffffu, bad == 0)) return;
-            if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
+            if (((++spins) & 15u) == 0 && check_abort(tag, t0)) {
                 dead = true;
                 return;
             }
@@ -908,7 +893,14 @@ struct Engine {
         for (int q = 0; q < 2; ++q)
 #pragma unroll
             for (int i = 0; i < NV; ++i) sacc[q][i] = 0.f;
-        int nstash = 0;                                       // stashes written (warp 0) / consumed (warps 4-7)
+        // landing buffer + mbarrier of this warp (gate warps: (y;x); residual and skip warps: y or a head vector)
+        uint2* land_base = reinterpret_cast<uint2*>(sm + pl.sm_land);
+        uint64_t* land_bar0 = reinterpret_cast<uint64_t*>(land_base + 2 * pl.land_z_pairs + 2 * pl.land_y_pairs);
+        const int lslot = warp == 0 ? 0 : (warp == 5 ? 1 : (warp == 1 ? 2 : 3));
+        uint2* land = land_base + (lslot < 2 ? lslot * pl.land_z_pairs : 2 * pl.land_z_pairs + (lslot - 2) * pl.land_y_pairs);
+        uint64_t* lbar = land_bar0 + lslot;
+        uint32_t lph = 0;
+        int nstash = 0;                                       // stashes written (warp 0) / consumed (warps 2-4)
         const bool prof = (pp.prof != nullptr) && tid == 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
 #define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
@@ -929,8 +921,8 @@ struct Engine {
                     const int e_in = pl.ex_yx + (s - 1) * YX;
                     WN_TICK(4);
                     if (s == 0) make_x0(v);
-                    else if (s == 1) { wpoll(xin, e_in, G2, tag_in, v); make_x0(v); }     // x_0 is known locally
-                    else wpoll(xin, e_in, YX, tag_in, v);
+                    else if (s == 1) { tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v); make_x0(v); }     // x_0 is known locally
+                    else tpoll(land, lbar, lph, xin, e_in, YX, tag_in, v);
                     WN_TICK(0);
                     for (int q = zidx; q < NQ_A; q += 2) {
                         float acc[NV];
@@ -970,8 +962,8 @@ struct Engine {
                 }
                 // stage L: warp 0 only forwards x_{L-1} to the older-tap warps
                 if (warp == 0 && !dead) {
-                    if (L == 1) { wpoll(xin, pl.ex_yx, G2, tagbase + wn_eid_yx(0), v); make_x0(v); }
-                    else wpoll(xin, pl.ex_yx + (L - 1) * YX, YX, tagbase + wn_eid_yx(L - 1), v);
+                    if (L == 1) { tpoll(land, lbar, lph, xin, pl.ex_yx, G2, tagbase + wn_eid_yx(0), v); make_x0(v); }
+                    else tpoll(land, lbar, lph, xin, pl.ex_yx + (L - 1) * YX, YX, tagbase + wn_eid_yx(L - 1), v);
                     wait_count<true>(s_ddone_cnt, 3 * (nstash - 1), 0x08000001u);
                     float* st = xs + (size_t)(L & 1) * YX * BT;
 #pragma unroll
@@ -1001,9 +993,9 @@ struct Engine {
                         float xprev = 0.f;
                         const int e_in = pl.ex_yx + (s - 1) * YX;
                         const uint32_t tag_in = tagbase + wn_eid_yx(s - 1);
-                        if (s >= 2) wpoll(xin, e_in, G2, tag_in, v, fin ? e_in + G2 + x0r + row : e_in, fin ? b : 0, &xprev);
+                        if (s >= 2) tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v, fin ? e_in + G2 + x0r + row : e_in, fin ? b : 0, &xprev);
                         else {
-                            wpoll(xin, e_in, G2, tag_in, v);
+                            tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v);
                             if (fin) {
                                 const int k = x0r + row;      // x_0 rows are computed locally
                                 if (pl.input_kind == 0) xprev = fmaf(first[k], s_in[b], first[R + k]);
@@ -1037,11 +1029,11 @@ struct Engine {
                 release_blob(t, 0);
                 for (int s = 1; s <= L && !dead; ++s) {
                     const bool tail = (s == L);
-                    const float* W = acquire_blob(t, s);
+                    const float* W = acquire_blob(t, s);     // (idempotent: a second acquire of the same blob just re-tests its barrier)
                     const int layer = s - 1;
                     if (roleS && tail) {
                         // the last layer's skip rows are on the critical path: read y_{L-1} straight from L2
-                        wpoll(xin, pl.ex_yx + (L - 1) * YX, G2, tagbase + wn_eid_yx(L - 1), v);
+                        tpoll(land, lbar, lph, xin, pl.ex_yx + (L - 1) * YX, G2, tagbase + wn_eid_yx(L - 1), v);
                         ++nstash;
                     } else {
                         wait_count<true>(s_stash_cnt, nstash + 1, 0x04000000u);
@@ -1100,8 +1092,9 @@ struct Engine {
             // ================================================================ head (wavenet.py:315-319), warps 0-3
             if (warp < WN_GW && !dead) {
                 const float* H = acquire_blob(t, L);
-                for (int q = warp; q < pl.NQ_HA; q += WN_GW) {
-                    wpoll(xin, pl.ex_sk, S, tagbase + wn_eid_sk(pl), v);
+                const int hslot = warp < 3 ? warp : 99;     // warps 0, 1, 2 own a landing buffer
+                for (int q = hslot; q < pl.NQ_HA; q += 3) {
+                    tpoll(land, lbar, lph, xin, pl.ex_sk, S, tagbase + wn_eid_sk(pl), v);
                     float acc[NV];
 #pragma unroll
                     for (int i = 0; i < NV; ++i) acc[i] = 0.f;
@@ -1111,9 +1104,9 @@ struct Engine {
                     if (holds_value() && row < na)
                         publish(pl.ex_h1 + a0 + row, my_b(), 0, fmaxf(acc[0] + H[pl.tb_Hab + row], 0.f), tagbase + wn_eid_h1(pl));
                 }
-                for (int q = warp; q < pl.NQ_HB; q += WN_GW) {
+                for (int q = hslot; q < pl.NQ_HB; q += 3) {
                     if (4 * q >= nb) break;
-                    wpoll(xin, pl.ex_h1, S, tagbase + wn_eid_h1(pl), v);
+                    tpoll(land, lbar, lph, xin, pl.ex_h1, S, tagbase + wn_eid_h1(pl), v);
                     float acc[NV];
 #pragma unroll
                     for (int i = 0; i < NV; ++i) acc[i] = 0.f;
@@ -1158,6 +1151,10 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) {
             mbar_init(&eng.bar_cfull[i], 1);
             mbar_init(&eng.bar_cempty[i], WN_NWARP - WN_GW);     // the warps that build the pre-sum table
+        }
+        {
+            uint64_t* lb = reinterpret_cast<uint64_t*>(reinterpret_cast<uint2*>(smem_raw + pl.sm_land) + 2 * pl.land_z_pairs + 2 * pl.land_y_pairs);
+            for (int i = 0; i < 4; ++i) mbar_init(lb + i, 1);
         }
         *eng.s_abort = 0;
         *eng.s_stash_cnt = 0;
