@@ -87,7 +87,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.head_kind = c.head_kind;
     pl.Kmix = (c.head_kind == WN_HEAD_SOFTMAX) ? 0 : (c.out_channels == 2 ? 1 : c.out_channels / 3);
     pl.skip_scale = (float)sqrt(1.0 / (double)c.layers);
-    pl.BT = batch <= 1 ? 1 : (batch <= 2 ? 2 : 4);      // utterances per launch (larger batches run in tiles)
+    pl.BT = batch <= 1 ? 1 : (batch <= 2 ? 2 : (batch <= 4 ? 4 : 8));
     const int BT = pl.BT;
 
     // ---- how many blocks: every block must own at least one gate pair
@@ -119,7 +119,8 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.fb_zb = o; o += pl.RA4;
     pl.fb_floats = align_up(o, 4);
     o = 0;
-    pl.lb_Zy = o; pl.lb_Zx = o; o += pl.NQ_A * (pl.G2 + pl.R) * 4;
+    pl.lb_Zy = o; o += pl.NQ_A * pl.G2 * 4;
+    pl.lb_Zx = o; o += pl.NQ_A * pl.R * 4;
     pl.lb_Xo = o; o += pl.NQ_BO * pl.G2 * 4;
     pl.lb_Td = o; o += pl.NQ_D * pl.R * 4;
     pl.lb_Sk = o; o += pl.NQ_BS * pl.G2 * 4;
@@ -146,20 +147,19 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     int nc = c.exchange_copies > 0 ? c.exchange_copies : env_int("WN_NCOPY", 0);
     // every (row, utterance) item of a broadcast is finalised by one thread per replica inside a
     // 64-thread group, so items * replicas <= 64
-    if (pl.NQ_BS > 2) return fail(WN_ERR_INVALID, "more than 8 skip rows per block (use more blocks)");
-    (void)nc;
-    pl.ncopy = 1;          // measured: scattered replica stores cost more than they save (profiles/r1_*)
+    const int max_items = std::max(std::max(pl.NYm, pl.NXm), std::max(pl.NSm, std::max(pl.NAm, pl.NBm))) * BT;
+    if (max_items > 64) return fail(WN_ERR_INVALID, "too many rows per block for this batch tile (use more blocks)");
+    if (nc <= 0) nc = 1;   // measured: scattered replica stores cost more than they save (profiles/r1_*)
+    nc = std::min(nc, 64 / max_items);
+    pl.ncopy = std::max(1, std::min(nc, P));
     if ((pl.G2 & 1) || (pl.R & 1) || (pl.S & 1))
-        return fail(WN_ERR_INVALID, "residual, gate/2 and skip channel counts must be even (16-byte bulk copies)");
-    if (pl.S > pl.G2 + pl.R) return fail(WN_ERR_INVALID, "skip_channels > residual + gate/2 is not supported");
+        return fail(WN_ERR_INVALID, "residual, gate/2 and skip channel counts must be even (16-byte exchange loads)");
     pl.ex_yx = 0;
     pl.ex_sk = pl.L * (pl.G2 + pl.R);
     pl.ex_h1 = pl.ex_sk + pl.S;
     pl.ex_h2 = pl.ex_h1 + pl.S;
-    pl.ex_elems = pl.ex_h2 + pl.O + (pl.O & 1);
-    pl.land_z_pairs = (pl.G2 + pl.R) * BT + 2;
-    pl.land_y_pairs = std::max(pl.G2, pl.S) * BT + 2;
-    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + 63) / 64) * 64 + 64;
+    pl.ex_elems = pl.ex_h2 + pl.O;
+    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + WN_XCHUNK - 1) / WN_XCHUNK + 1) * WN_XSTRIDE + 96;
 
     // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later
     ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);
@@ -200,7 +200,6 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_noise = take((long long)BT * (pl.O + 2) * 4, 16);
         pl.sm_first = take(2LL * pl.R * 4, 16);
         pl.sm_ring = take(ring_smem ? ring_bytes : 16, 16);
-        pl.sm_land = take((2LL * pl.land_z_pairs + 2LL * pl.land_y_pairs) * 8 + 64, 128);   // TMA landing buffers + 4 mbarriers
         pl.sm_slots = take(0, 128);
         return off;
     };
@@ -356,8 +355,8 @@ static void pack_cta(const WnPlan& pl, const wn_weights& w, const Folded& f, int
         const wn_layer_weights& pw = w.layers[s - 1];
         for (int rr = 0; rr < 2 * ny; ++rr) {
             const int g = grow(rr);
-            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Zy, G2 + R, rr, k, f.M[s - 1][(size_t)g * G2 + k]);
-            for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Zy, G2 + R, rr, G2 + k, f.V[s][(size_t)g * R + k]);
+            for (int k = 0; k < G2; ++k) put_q(blob + pl.lb_Zy, G2, rr, k, f.M[s - 1][(size_t)g * G2 + k]);
+            for (int k = 0; k < R; ++k) put_q(blob + pl.lb_Zx, R, rr, k, f.V[s][(size_t)g * R + k]);
             blob[pl.lb_zb + rr] = f.zb[s][g];
         }
         for (int r = 0; r < nx; ++r) {
@@ -432,7 +431,7 @@ struct WnHandle {
     cudaStream_t last_stream = nullptr;
     bool pending = false;
     int64_t launches = 0;
-    bool attr_set[20] = {};
+    bool attr_set[16] = {};
 };
 
 template <typename T>
@@ -525,24 +524,24 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     }
 
     void* kargs[2] = {(void*)&pl, (void*)&pp};
-    // kernel variants: <batch tile, elements of a broadcast vector per lane (one warp reads a whole vector)>
-    const int need = (std::max(pl.G2 + pl.R, pl.S) + 31) / 32;
-    const int var = need <= 4 ? 0 : (need <= 8 ? 1 : (need <= 16 ? 2 : (need <= 24 ? 3 : 4)));
-    if (need > 64) return fail(WN_ERR_INVALID, "broadcast vector too long for one warp (unsupported shape)");
+    // kernel variants: <batch tile, elements of x per thread, elements of y per thread> (128-thread groups)
+    auto efor = [](int K) { return K <= 128 ? 1 : (K <= 256 ? 2 : (K <= 512 ? 4 : 8)); };
+    const int er = efor(pl.R), eg = efor(pl.G2);
+    const int var = (er == 1 && eg == 1) ? 0 : ((er <= 2 && eg <= 2) ? 1 : ((er <= 4 && eg <= 2) ? 2 : 3));
     const void* fn = nullptr;
-    if (var == 4 && BT > 1) return fail(WN_ERR_INVALID, "this shape is only built for one utterance per launch (WN_MAX_TILE=1)");
 #define WN_PICK(BT_)                                                                          \
-    fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 4>                             \
-       : var == 1 ? (const void*)wn::wn_persistent_kernel<BT_, 8>                             \
-       : var == 2 ? (const void*)wn::wn_persistent_kernel<BT_, 16>                            \
-                  : (const void*)wn::wn_persistent_kernel<BT_, 24>
+    fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 1, 1>                          \
+       : var == 1 ? (const void*)wn::wn_persistent_kernel<BT_, 2, 2>                          \
+       : var == 2 ? (const void*)wn::wn_persistent_kernel<BT_, 4, 2>                          \
+                  : (const void*)wn::wn_persistent_kernel<BT_, 8, 8>
     switch (BT) {
-        case 1: if (var == 4) fn = (const void*)wn::wn_persistent_kernel<1, 64>; else { WN_PICK(1); } break;
+        case 1: WN_PICK(1); break;
         case 2: WN_PICK(2); break;
-        default: WN_PICK(4); break;
+        case 4: WN_PICK(4); break;
+        default: WN_PICK(8); break;
     }
 #undef WN_PICK
-    const int ai = bt_index(BT) * 5 + var;
+    const int ai = bt_index(BT) * 4 + var;
     if (!h->attr_set[ai]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
         h->attr_set[ai] = true;
@@ -735,7 +734,7 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
     cudaStream_t st = (cudaStream_t)a->stream;
     // batch tiles: 8 utterances per launch spill registers in this build (168/thread with 10 warps), so
     // the default tile is 4 (measured faster per utterance, profiles/r1_*sweep*); WN_MAX_TILE=8 overrides
-    const int tile = std::max(1, std::min(4, env_int("WN_MAX_TILE", 4)));
+    const int tile = std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)));
     for (int b0 = 0; b0 < a->B; b0 += tile) {
         const int Bc = std::min(tile, a->B - b0);
         rc = launch_chunk(h, a, b0, Bc, st);
@@ -782,7 +781,7 @@ int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out) {
     if (!h || !out) return fail(WN_ERR_INVALID, "null argument");
     WnPlan pl;
     std::vector<int> rt;
-    int32_t rc = build_plan(h->cfg, std::min(batch, std::max(1, std::min(4, env_int("WN_MAX_TILE", 4)))), h->num_sms, h->smem_cap, pl, rt);
+    int32_t rc = build_plan(h->cfg, std::min(batch, std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)))), h->num_sms, h->smem_cap, pl, rt);
     if (rc) return rc;
     fill_info(h->cfg, pl, out);
     out->launches = h->launches;

@@ -123,14 +123,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ uint2 ld_pair(const uint2* p) {
     uint2 v;
-    // weak, L2-coherent (.cg bypasses L1): unlike ld.relaxed.gpu, several of these from one thread overlap.
-    // Data and tag share one 8-byte word, so no ordering between different loads is needed.
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint4 ld_pair2(const uint2* p) {
     uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p)
                  : "memory");
@@ -283,9 +281,10 @@ __device__ __noinline__ bool wn_check_abort(volatile int* s_abort, int* err, lon
         default: { constexpr int E = 8; __VA_ARGS__ } break;  \
     }
 
-template <int BT, int EK>
+template <int BT, int ER, int EG>
 struct Engine {
     static constexpr int NV = 4 * BT;
+    static constexpr int NA = (BT >= 8) ? 1 : 2;     // quads reduced together (their shuffle chains overlap)
     const WnPlan& pl;
     const WnPtrs& pp;
     unsigned char* sm;
@@ -296,7 +295,7 @@ struct Engine {
     volatile int* s_stash_cnt;     // stashes published by the critical group (monotonic)
     volatile int* s_ddone_cnt;     // deferred-group warps finished, summed over stages (monotonic)
     int* ringtab;
-    float *xs, *red1, *red2, *sb, *pre, *cond, *skipacc, *hs, *noise, *first, *slots;
+    float *xs, *ys, *red1, *red2, *sb, *pre, *cond, *skipacc, *hs, *noise, *first, *slots;
     volatile float* ring;
     float* s_in;     // [BT] scalar feedback
     int* s_idx;      // [BT] class feedback
@@ -324,6 +323,7 @@ struct Engine {
         s_dense = reinterpret_cast<float*>(s_idx + BT);
         ringtab = reinterpret_cast<int*>(sm + pl.sm_ringtab);
         xs = reinterpret_cast<float*>(sm + pl.sm_xs);
+        ys = xs + 2 * pl.R * BT;
         red1 = reinterpret_cast<float*>(sm + pl.sm_red1);
         red2 = reinterpret_cast<float*>(sm + pl.sm_red2);
         sb = reinterpret_cast<float*>(sm + pl.sm_sb);
@@ -372,29 +372,61 @@ struct Engine {
         __threadfence_block();
     }
 
-    // ---- wait for a broadcast vector with the 128 threads of warps 0-3: thread owns k = gt + j*128
+    // ---- wait for a broadcast vector: thread owns elements k = gt + j*WN_NTC.
+    // Which element of a K-vector is slot j of this thread.  With one utterance per launch a thread owns
+    // PAIRS of adjacent elements so that one 16-byte load fetches two (value, tag) pairs: every L1-bypassing
+    // coherent load costs the issuing warp ~250 cycles and they do not overlap (profiles/r1_v4_*), so the
+    // number of loads per thread is what sets the poll time.
+    template <int E>
+    __device__ __forceinline__ int elem(int j) const {
+        if constexpr (BT == 1 && (E % 2) == 0) return 2 * gt + 2 * WN_NTC * (j >> 1) + (j & 1);
+        else return gt + j * WN_NTC;
+    }
     // `src` is the base of the block's replica, `e0` the first element of the vector
     template <int E>
     __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
                                                  float (&x)[E][BT]) {
         uint32_t bad = 0;
-        uint2 raw[E][BT];
+        if constexpr (BT == 1 && (E % 2) == 0) {
+            uint4 raw[E / 2];
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int k = gt + j * WN_NTC;
+            for (int j = 0; j < E / 2; ++j) {
+                const int k = elem<E>(2 * j);
+                raw[j] = make_uint4(0u, tag, 0u, tag);
+                if (k < K) raw[j] = ld_pair2(src + wn_pair_index((long long)(e0 + k)));
+            }
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                raw[j][b] = make_uint2(0u, tag);
-                if (k < K) raw[j][b] = ld_pair(src + wn_pair_index((long long)(e0 + k) * BT + b));
+            for (int j = 0; j < E / 2; ++j) {
+                bad |= (raw[j].y ^ tag) | ((elem<E>(2 * j) + 1 < K) ? (raw[j].w ^ tag) : 0u);
+                x[2 * j][0] = __uint_as_float(raw[j].x);
+                x[2 * j + 1][0] = __uint_as_float(raw[j].z);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int k = elem<E>(j);
+                if (k < K) {
+                    const uint2* s = src + wn_pair_index((long long)(e0 + k) * BT);
+                    if constexpr (BT == 1) {
+                        const uint2 v = ld_pair(s);
+                        x[j][0] = __uint_as_float(v.x);
+                        bad |= v.y ^ tag;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BT; b += 2) {
+                            const uint4 v = ld_pair2(s + b);
+                            x[j][b] = __uint_as_float(v.x);
+                            bad |= v.y ^ tag;
+                            x[j][b + 1] = __uint_as_float(v.z);
+                            bad |= v.w ^ tag;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+                }
             }
         }
-#pragma unroll
-        for (int j = 0; j < E; ++j)
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                bad |= raw[j][b].y ^ tag;
-                x[j][b] = __uint_as_float(raw[j][b].x);
-            }
         return bad;
     }
     template <int E>
@@ -409,15 +441,88 @@ struct Engine {
             }
         }
     }
+    // two vectors of the same exchange (y then x): all loads of an attempt are in flight together
+    template <int EA, int EB>
+    __device__ __forceinline__ void poll_vec2(const uint2* __restrict__ src, int ea, int KA, float (&a)[EA][BT],
+                                              int eb, int KB, float (&b)[EB][BT], uint32_t tag) {
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (true) {
+            const uint32_t bad = load_vec<EA>(src, ea, KA, tag, a) | load_vec<EB>(src, eb, KB, tag, b);
+            if (bad == 0) return;
+            if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
+                dead = true;
+                return;
+            }
+        }
+    }
     template <int E>
     __device__ __forceinline__ void stash(float* dst, int K, const float (&x)[E][BT]) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            const int k = gt + j * WN_NTC;
+            const int k = elem<E>(j);
             if (k < K) {
 #pragma unroll
                 for (int b = 0; b < BT; ++b) dst[k * BT + b] = x[j][b];
             }
+        }
+    }
+    template <int E>
+    __device__ __forceinline__ void unstash(const float* src, int K, float (&x)[E][BT]) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = elem<E>(j);
+#pragma unroll
+            for (int b = 0; b < BT; ++b) x[j][b] = (k < K) ? src[k * BT + b] : 0.f;
+        }
+    }
+
+    // ---- one row quad (4 rows x K) times the thread's slice of the input vector, accumulated
+    template <int E>
+    __device__ __forceinline__ void quad_fma(const float* __restrict__ wq /* [K][4] */, int K,
+                                             const float (&x)[E][BT], float (&acc)[NV]) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = elem<E>(j);
+            if (k < K) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wq + (size_t)k * 4);
+#pragma unroll
+                for (int b = 0; b < BT; ++b) {
+                    acc[0 * BT + b] = fmaf(w4.x, x[j][b], acc[0 * BT + b]);
+                    acc[1 * BT + b] = fmaf(w4.y, x[j][b], acc[1 * BT + b]);
+                    acc[2 * BT + b] = fmaf(w4.z, x[j][b], acc[2 * BT + b]);
+                    acc[3 * BT + b] = fmaf(w4.w, x[j][b], acc[3 * BT + b]);
+                }
+            }
+        }
+    }
+    // after the warp reduction lane (v << (5-M)) holds value v of the quad; warp gw's partial goes
+    // to red[(q*NV + v)*4 + gw]
+    __device__ __forceinline__ void quad_store(const float (&acc)[NV], int q, float* __restrict__ red) {
+        constexpr int M = ilog2c(NV);
+        if ((lane & ((32 >> M) - 1)) == 0) red[(q * NV + (lane >> (5 - M))) * WN_GW + gw] = acc[0];
+    }
+    __device__ __forceinline__ float red_sum(const float* red, int rowidx, int b) const {
+        const int v = (rowidx >> 2) * NV + (rowidx & 3) * BT + b;
+        const float4 a = *reinterpret_cast<const float4*>(red + v * WN_GW);
+        return (a.x + a.y) + (a.z + a.w);
+    }
+    // simple GEMV over NQ quads, two quads per pass so that their shuffle chains overlap
+    template <int E>
+    __device__ __forceinline__ void gemv(const float* __restrict__ w, int NQ, int K, const float (&x)[E][BT],
+                                         float* __restrict__ red, int q0 = 0) {
+        for (int q = 0; q < NQ; q += NA) {
+            float acc[NA][NV];
+#pragma unroll
+            for (int h = 0; h < NA; ++h) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
+                if (q + h < NQ) quad_fma<E>(w + (size_t)(q + h) * K * 4, K, x, acc[h]);
+            }
+            reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+            for (int h = 0; h < NA; ++h)
+                if (q + h < NQ) quad_store(acc[h], q0 + q + h, red);
         }
     }
     __device__ __forceinline__ void publish(int elem, int b, int copy, float v, uint32_t tag) {
@@ -697,120 +802,42 @@ struct Engine {
     }
 
     // ======================================================================================
-    // compute warps.  Every row quad of a stage belongs to ONE warp, which polls the inputs it needs
-    // into registers (lane owns elements e = lane + 32 j), multiplies, butterfly-reduces inside the
-    // warp, finalises and publishes: no cross-warp partial sums and no block barrier between two
-    // broadcasts.  Roles (warp index): 0 and 5 gate quads, 1 residual quads (these poll L2 directly and are
-    // the critical path), 2 skip quads, 3-4 queued older-tap quads (fed from a shared-memory stash that
-    // warp 0 writes AFTER it has published, i.e. while the broadcast is in flight); warp 6 streams the
-    // weights (TMA), warp 7 projects the local conditioning.  8 warps -> 255 registers per thread.
+    // compute groups
     // ======================================================================================
     __device__ __forceinline__ static int efor(int K) {
         return K <= WN_NTC ? 1 : (K <= 2 * WN_NTC ? 2 : (K <= 4 * WN_NTC ? 4 : 8));
     }
 
-    // Wait for a broadcast vector: ONE TMA bulk copy (cp.async.bulk, reads through L2 and never L1, fully
-    // pipelined by the copy engine) lands the K*BT pairs in a warp-private shared-memory buffer; the lanes
-    // then check the tags there and the copy is re-issued until every pair carries this exchange's tag.
-    // (L1-bypassing loads issued by the warp itself cost ~250 cycles EACH, profiles/r1_*: 24 per lane = 6000.)
-    // `xe` >= 0 additionally fetches one element (for utterance xb) into `xv` with an ordinary coherent load.
-    __device__ __forceinline__ void tpoll(uint2* land, uint64_t* bar, uint32_t& ph, const uint2* __restrict__ src,
-                                          int e0, int K, uint32_t tag, float (&v)[EK][BT], int xe = -1, int xb = 0,
-                                          float* xv = nullptr) {
-        uint32_t spins = 0;
-        long long t0 = 0;
-        const uint32_t bytes = ((uint32_t)(K * BT) * 8u + 15u) & ~15u;
-        while (true) {
-            if (lane == 0) {
-                mbar_expect_tx(bar, bytes);
-                bulk_g2s(land, src + (size_t)e0 * BT, bytes, bar);
-            }
-            uint32_t bad = 0;
-            if (xe >= 0) {
-                const uint2 w = ld_pair(src + ((size_t)xe * BT + xb));
-                *xv = __uint_as_float(w.x);
-                bad |= w.y ^ tag;
-            }
-            while (!mbar_try_wait(bar, ph)) {
-                if (((++spins) & 255u) == 0 && check_abort(tag, t0)) {
-                    dead = true;
-                    return;
-                }
-            }
-            ph ^= 1u;
+    // x_0 = first 1x1 conv of the fed-back sample (wavenet.py:308); every block computes all of it
+    __device__ __forceinline__ void make_x0(float (&x)[ER][BT]) {
+        const int R = pl.R, O = pl.O;
 #pragma unroll
-            for (int j = 0; j < EK; ++j) {
-                const int e = lane + 32 * j;
-                if (e < K) {
+        for (int j = 0; j < ER; ++j) {
+            const int k = elem<ER>(j);
 #pragma unroll
-                    for (int b = 0; b < BT; ++b) {
-                        const uint2 w = land[e * BT + b];
-                        v[j][b] = __uint_as_float(w.x);
-                        bad |= w.y ^ tag;
-                    }
-                }
-            }
-            if (__all_sync(0xffffffffu, bad == 0)) return;
-            if (((++spins) & 15u) == 0 && check_abort(tag, t0)) {
-                dead = true;
-                return;
-            }
-        }
-    }
-    // acc += W_quad[k] * v for the lane's elements; the quad's weights are [k][4] starting at w, the lane's
-    // element e uses k = e - kbase when kbase <= e < kbase + K
-    __device__ __forceinline__ void wfma(const float* __restrict__ w, int kbase, int K, const float (&v)[EK][BT],
-                                         float (&acc)[NV]) {
-#pragma unroll
-        for (int j = 0; j < EK; ++j) {
-            const int k = lane + 32 * j - kbase;
-            if (k >= 0 && k < K) {
-                const float4 w4 = *reinterpret_cast<const float4*>(w + (size_t)k * 4);
-#pragma unroll
-                for (int b = 0; b < BT; ++b) {
-                    acc[0 * BT + b] = fmaf(w4.x, v[j][b], acc[0 * BT + b]);
-                    acc[1 * BT + b] = fmaf(w4.y, v[j][b], acc[1 * BT + b]);
-                    acc[2 * BT + b] = fmaf(w4.z, v[j][b], acc[2 * BT + b]);
-                    acc[3 * BT + b] = fmaf(w4.w, v[j][b], acc[3 * BT + b]);
-                }
-            }
-        }
-    }
-    // After reduce_scatter<NV> lane (v * LPV) holds value v = row_in_quad*BT + b; LPV lanes per value.
-    static constexpr int LPV = 32 / NV;
-    __device__ __forceinline__ bool holds_value() const { return (lane % LPV) == 0; }
-    __device__ __forceinline__ int my_row() const { return (lane / LPV) / BT; }   // row inside the quad
-    __device__ __forceinline__ int my_b() const { return (lane / LPV) % BT; }
-
-    // x_0 = first 1x1 conv of the fed-back sample (wavenet.py:308) for the lane's elements of the
-    // [y ; x] vector space (x part starts at element G2); every block computes all of it
-    __device__ __forceinline__ void make_x0(float (&v)[EK][BT]) {
-        const int R = pl.R, O = pl.O, G2 = pl.G2;
-#pragma unroll
-        for (int j = 0; j < EK; ++j) {
-            const int k = lane + 32 * j - G2;
-            if (k >= 0 && k < R) {
+            for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
+            if (k < R) {
                 if (pl.input_kind == 0) {
 #pragma unroll
-                    for (int b = 0; b < BT; ++b) v[j][b] = fmaf(first[k], s_in[b], first[R + k]);
+                    for (int b = 0; b < BT; ++b) x[j][b] = fmaf(first[k], s_in[b], first[R + k]);
                 } else {
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
                         const int idx = s_idx[b];
                         if (idx >= 0) {
-                            v[j][b] = __ldg(pp.first_w + (size_t)idx * R + k) + first[R + k];   // one-hot: column gather
+                            // one-hot input: the GEMV is a column gather
+                            x[j][b] = __ldg(pp.first_w + (size_t)idx * R + k) + first[R + k];
                         } else {
                             float a = 0.f;
                             for (int o = 0; o < O; ++o)
                                 a = fmaf(__ldg(pp.first_w + (size_t)o * R + k), s_dense[b * O + o], a);
-                            v[j][b] = a + first[R + k];
+                            x[j][b] = a + first[R + k];
                         }
                     }
                 }
             }
         }
     }
-
     // modules.py:154  tanh(a) * sigmoid(g) with a single division:
     //   (1 - e^{-2a}) / ((1 + e^{-2a}) (1 + e^{-g}));  |a| is clamped where tanh has saturated in fp32.
     // Absolute error ~1e-7 (the subtraction 1 - e^{-2a} loses relative, not absolute, accuracy near 0).
@@ -819,37 +846,244 @@ struct Engine {
         const float ea = expf(-2.0f * ac), eg = expf(-g);
         return (1.0f - ea) / ((1.0f + ea) * (1.0f + eg));
     }
-
     // Everything of z_l(t) that does not depend on step t's broadcasts: (folded) bias + global conditioning
-    // + local conditioning projection + the queued products of the older taps, for all layers of step t.
-    // Built between two block barriers at the end of step t-1 by the warps that are not sampling.
-    __device__ void build_pre(int t, int first_thread, int nthreads) {
+    // + local conditioning projection + the queued products of the older taps.  The deferred group builds
+    // the whole table for step `t` while the critical group is still in the head of step t-1.
+    __device__ void build_pre(int t) {
         const int L = pl.L, RA4 = pl.RA4, kw = pl.kw, n = L * pl.RA * BT;
         if (pl.C > 0) {
             if (!wait_bar<true>(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x10000000u)) dead = true;
         }
         const float* cd = cond + (size_t)(t & 1) * L * RA4 * BT;
-        for (int i = tid - first_thread; i < n; i += nthreads) {
+        for (int i = gt; i < n; i += WN_NTC) {
             const int b = i % BT, rr = (i / BT) % pl.RA, l = i / (BT * pl.RA);
             const int idx = (l * RA4 + rr) * BT + b;
             float v = sb[idx];
             if (pl.C > 0) v += cd[idx];
             for (int k = 0; k < kw - 1; ++k) {
                 const int e = (l * (kw - 1) + k) * 3;
-                v += ring[((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT + rr * BT + b];   // offset + (t mod delay)
+                int pos = ringtab[e + 2];
+                if (t > 0) { ++pos; if (pos == ringtab[e + 1]) pos = 0; }     // the table still holds (t-1) mod delay
+                v += ring[((size_t)ringtab[e] + pos) * RA4 * BT + rr * BT + b];
             }
             pre[idx] = v;
         }
         __syncwarp();
-        // the conditioning warp may refill cond[t&1] once every building warp is done with it
-        if (pl.C > 0 && lane == 0) mbar_arrive(&bar_cempty[t & 1]);
+        if (pl.C > 0) {
+            // the conditioning warp may refill cond[t&1] once all four deferred warps are done with it
+            if (lane == 0) mbar_arrive(&bar_cempty[t & 1]);
+        }
     }
 
-    // end of a step: (a) everyone is done with step t -> sampler (one warp per utterance) while the
-    // other threads advance the ring positions -> (b) -> pre-sums of step t+1 -> (c)
-    __device__ __forceinline__ bool step_end(int t, bool step_dead) {
+    // --------------------------------------------------------------------------------------
+    // critical group (warps 0-3)
+    // --------------------------------------------------------------------------------------
+    __device__ void crit_loop() {
+        const int L = pl.L, R = pl.R, G2 = pl.G2, S = pl.S, O = pl.O, T = pp.T, P = pl.P, ncopy = pl.ncopy;
+        int y0, ny, x0r, nx, s0, ns, a0, na, b0, nb;
+        wn_part(G2, P, p, y0, ny);
+        wn_part(R, P, p, x0r, nx);
+        wn_part(S, P, p, s0, ns);
+        wn_part(S, P, p, a0, na);
+        wn_part(O, P, p, b0, nb);
+        const int ES = efor(S), EO = efor(O);
+        const uint2* xin = pp.xbuf + (size_t)(p % ncopy) * pl.copy_stride_pairs;
+        const uint32_t NEID = (uint32_t)L + 3u;
+        const int YX = G2 + R;
+        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
+        const int NQ_A = pl.NQ_A, NQ_BO = pl.NQ_BO, nqc = NQ_A + NQ_BO;
+        // finalizer roles: threads [0,64) publish gate outputs (and skip / head rows), [64,128) the
+        // residual rows; local index u -> (item, replica)
+        const int fl = gt & 63;
+        const bool grpA = gt < 64;
+        auto role = [&](int nitems, int& item, int& copy) {
+            item = -1; copy = 0;
+            if (nitems > 0 && fl < nitems * ncopy) { item = fl % nitems; copy = fl / nitems; }
+        };
+        int it_y, cp_y, it_x, cp_x, it_s, cp_s, it_a, cp_a, it_b, cp_b;
+        role(ny * BT, it_y, cp_y);
+        role(nx * BT, it_x, cp_x);
+        role(ns * BT, it_s, cp_s);
+        role(na * BT, it_a, cp_a);
+        role(nb * BT, it_b, cp_b);
+        if (!grpA) it_y = it_s = it_a = it_b = -1;
+        if (grpA) it_x = -1;
+        const int pa_idx = it_y >= 0 ? (2 * (it_y / BT)) * BT + (it_y % BT) : 0;   // [row a_j][b]; row b_j is BT further
+        float xr[ER][BT], yr[EG][BT];
+        const bool prof = (pp.prof != nullptr) && tid == 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+#define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
+        int nstash = 0;      // stashes published so far == deferred stages started
+        int ndone = 0;       // deferred stages this group has waited for
+        if (bar_or_n<3, WN_NT>(false)) return;      // the deferred group has built the pre-sums of step 0
+
+        for (int t = 0; t < T; ++t) {
+            const uint32_t tagbase = (uint32_t)t * NEID + 1u;
+            if (prof) tc = clock64();
+            bool step_dead = false;
+            do {
+                make_x0(xr);
+                WN_TICK(7);
+                // ------------------------------------------------------------ stage 0: layer 0 from x_0
+                {
+                    const float* W = acquire_blob(t, 0);
+                    float pre_a = 0.f, pre_b = 0.f;
+                    if (it_y >= 0) { pre_a = pre[pa_idx]; pre_b = pre[pa_idx + BT]; }
+                    float* r1 = red1;                                   // partials buffers alternate by stage
+                    gemv<ER>(W + pl.fb_Zx, NQ_A, R, xr, r1);
+                    WN_TICK(1);
+                    if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                    WN_TICK(2);
+                    if (it_y >= 0) {
+                        const int fr = it_y / BT, fb = it_y % BT;
+                        const float a = red_sum(r1, 2 * fr, fb) + pre_a;
+                        const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
+                        publish(pl.ex_yx + y0 + fr, fb, cp_y, gate(a, g), tagbase + wn_eid_yx(0));
+                    }
+                    release_blob(t, 0);
+                    WN_TICK(3);
+                }
+                // ------------------------------------------------------------ stages 1..L-1
+                for (int s = 1; s < L; ++s) {
+                    const float* W = acquire_blob(t, s);
+                    float pre_a = 0.f, pre_b = 0.f;
+                    if (it_y >= 0) { pre_a = pre[pa_idx + s * pl.RA4 * BT]; pre_b = pre[pa_idx + s * pl.RA4 * BT + BT]; }
+                    WN_TICK(4);
+                    {
+                        const int e0 = pl.ex_yx + (s - 1) * YX;
+                        const uint32_t tag = tagbase + wn_eid_yx(s - 1);
+                        if (s >= 2) poll_vec2<EG, ER>(xin, e0, G2, yr, e0 + G2, R, xr, tag);
+                        else poll_vec<EG>(xin, e0, G2, tag, yr);      // x_0 is already in registers
+                    }
+                    WN_TICK(0);
+                    float* xst = xs + (size_t)(s & 1) * R * BT;
+                    float* r1 = red1 + (size_t)(s & 1) * pl.red1_floats;
+                    stash<ER>(xst, R, xr);
+                    stash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
+                    // gate pre-activations of layer s (quads [0,NQ_A)) and residual rows x_s (quads [NQ_A,nqc))
+                    for (int q = 0; q < nqc; q += NA) {
+                        float acc[NA][NV];
+#pragma unroll
+                        for (int h = 0; h < NA; ++h) {
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
+                            const int qq = q + h;
+                            if (qq < NQ_A) {
+                                quad_fma<EG>(W + pl.lb_Zy + (size_t)qq * G2 * 4, G2, yr, acc[h]);
+                                quad_fma<ER>(W + pl.lb_Zx + (size_t)qq * R * 4, R, xr, acc[h]);
+                            } else if (qq < nqc) {
+                                quad_fma<EG>(W + pl.lb_Xo + (size_t)(qq - NQ_A) * G2 * 4, G2, yr, acc[h]);
+                            }
+                        }
+                        reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+                        for (int h = 0; h < NA; ++h)
+                            if (q + h < nqc) quad_store(acc[h], q + h, r1);
+                    }
+                    WN_TICK(1);
+                    if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                    if (gt == 0) {          // stash complete (the barrier ordered every thread's writes)
+                        __threadfence_block();
+                        *s_stash_cnt = nstash + 1;
+                    }
+                    ++nstash;
+                    WN_TICK(2);
+                    const uint32_t tag = tagbase + wn_eid_yx(s);
+                    if (it_y >= 0) {
+                        const int fr = it_y / BT, fb = it_y % BT;
+                        const float a = red_sum(r1, 2 * fr, fb) + pre_a;
+                        const float g = red_sum(r1, 2 * fr + 1, fb) + pre_b;
+                        publish(pl.ex_yx + s * YX + y0 + fr, fb, cp_y, gate(a, g), tag);
+                    }
+                    if (it_x >= 0) {
+                        // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
+                        const int fr = it_x / BT, fb = it_x % BT;
+                        const float o = red_sum(r1, NQ_A * 4 + fr, fb) + W[pl.lb_xb + fr];
+                        publish(pl.ex_yx + s * YX + G2 + x0r + fr, fb, cp_x, (o + xst[(x0r + fr) * BT + fb]) * RSQRT2, tag);
+                    }
+                    release_blob(t, s);
+                    // the stash of stage s+1 reuses the buffer of stage s-1: the deferred group must be done with it
+                    if (s >= 2) { wait_count(s_ddone_cnt, WN_GW * (ndone + 1), 0x08000000u); ++ndone; }
+                    WN_TICK(3);
+                }
+                if (step_dead) break;
+                // ------------------------------------------------------------ stage L: skip of the last layer
+                const float* H = acquire_blob(t, L);
+                {
+                    const int e0 = pl.ex_yx + (L - 1) * YX;
+                    const uint32_t tag = tagbase + wn_eid_yx(L - 1);
+                    if (L >= 2) poll_vec2<EG, ER>(xin, e0, G2, yr, e0 + G2, R, xr, tag);
+                    else poll_vec<EG>(xin, e0, G2, tag, yr);
+                }
+                WN_TICK(0);
+                stash<ER>(xs + (size_t)(L & 1) * R * BT, R, xr);
+                float* r1 = red1 + (size_t)(L & 1) * pl.red1_floats;
+                gemv<EG>(H + pl.tb_Sk, pl.NQ_BS, G2, yr, r1);
+                WN_TICK(1);
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (gt == 0) {
+                    __threadfence_block();
+                    *s_stash_cnt = nstash + 1;
+                }
+                ++nstash;
+                // skip rows of layers 0..L-2 were accumulated by the deferred group: wait for its stage L-1
+                if (L >= 2) { wait_count(s_ddone_cnt, WN_GW * (ndone + 1), 0x08000001u); ++ndone; }
+                WN_TICK(2);
+                if (it_s >= 0) {
+                    // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
+                    const int fr = it_s / BT, fb = it_s % BT;
+                    float tot = red_sum(r1, fr, fb) + H[pl.tb_sb + fr];
+                    if (L >= 2) tot = skipacc[it_s] + tot;
+                    publish(pl.ex_sk + s0 + fr, fb, cp_s, fmaxf(tot * pl.skip_scale, 0.f), tagbase + wn_eid_sk(pl));
+                }
+                WN_TICK(3);
+                // ---------------------------------------------------------------- head (wavenet.py:315-319)
+                float* r1a = red1 + (size_t)((L + 1) & 1) * pl.red1_floats;
+                if (na > 0) {
+                    WN_DISPATCH_E(ES, { float h[E][BT];
+                                        poll_vec<E>(xin, pl.ex_sk, S, tagbase + wn_eid_sk(pl), h);
+                                        gemv<E>(H + pl.tb_Ha, pl.NQ_HA, S, h, r1a); });
+                }
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (it_a >= 0) {
+                    const int fr = it_a / BT, fb = it_a % BT;
+                    publish(pl.ex_h1 + a0 + fr, fb, cp_a, fmaxf(red_sum(r1a, fr, fb) + H[pl.tb_Hab + fr], 0.f), tagbase + wn_eid_h1(pl));
+                }
+                if (nb > 0) {
+                    WN_DISPATCH_E(ES, { float h[E][BT];
+                                        poll_vec<E>(xin, pl.ex_h1, S, tagbase + wn_eid_h1(pl), h);
+                                        gemv<E>(H + pl.tb_Hb, pl.NQ_HB, S, h, r1); });
+                }
+                if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
+                if (it_b >= 0) {
+                    const int fr = it_b / BT, fb = it_b % BT;
+                    publish(pl.ex_h2 + b0 + fr, fb, cp_b, red_sum(r1, fr, fb) + H[pl.tb_Hbb + fr], tagbase + wn_eid_h2(pl));
+                }
+                release_blob(t, L);
+                {
+                    WN_DISPATCH_E(EO, { float h[E][BT];
+                                        poll_vec<E>(xin, pl.ex_h2, O, tagbase + wn_eid_h2(pl), h);
+                                        stash<E>(hs, O, h); });
+                }
+                WN_TICK(5);
+            } while (false);
+            // ---- both groups meet: sampler (one warp per utterance), then the next step
+            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            // the deferred group finished its stage L before this barrier
+            if (L >= 1) ++ndone;
+            step_tail(t);
+            if (bar_or_n<3, WN_NT>(false)) return;
+            WN_TICK(6);
+        }
+        if (prof) {
+            for (int i = 0; i < 8; ++i) pp.prof[(size_t)p * 16 + i] = pc[i];
+        }
+#undef WN_TICK
+    }
+
+    // head outputs are in hs: optional dump, sampling, feedback for the next step (all 8 compute warps)
+    __device__ __forceinline__ void step_tail(int t) {
         const int O = pl.O, T = pp.T;
-        if (bar_or_n<3, WN_NT>(dead || step_dead)) return true;
         if (p == 0 && pp.params_out != nullptr) {
             for (int i = tid; i < O * BT; i += WN_NT) {
                 const int o = i / BT, b = i % BT;
@@ -862,274 +1096,107 @@ struct Engine {
             sample_utt(t, warp);
             if (t + 1 < T) fetch_noise(t + 1, warp);
         }
-        for (int i = WN_NT - 1 - tid; i < pl.L * (pl.kw - 1); i += WN_NT) {   // positions -> (t+1) mod delay
+        // advance the ring positions to (t+1) mod delay
+        for (int i = WN_NT - 1 - tid; i < pl.L * (pl.kw - 1); i += WN_NT) {
             const int pos = ringtab[i * 3 + 2] + 1;
             ringtab[i * 3 + 2] = (pos == ringtab[i * 3 + 1]) ? 0 : pos;
         }
-        if (bar_or_n<3, WN_NT>(false)) return true;
-        if (t + 1 < T && warp >= WN_GW) build_pre(t + 1, WN_NTC, WN_NT - WN_NTC);
-        return bar_or_n<3, WN_NT>(dead);
     }
 
-    __device__ void compute_loop() {
-        const int L = pl.L, R = pl.R, G2 = pl.G2, S = pl.S, O = pl.O, T = pp.T, P = pl.P, kw = pl.kw;
-        int y0, ny, x0r, nx, s0, ns, a0, na, b0, nb;
-        wn_part(G2, P, p, y0, ny);
-        wn_part(R, P, p, x0r, nx);
-        wn_part(S, P, p, s0, ns);
-        wn_part(S, P, p, a0, na);
-        wn_part(O, P, p, b0, nb);
-        const uint2* xin = pp.xbuf + (size_t)(p % pl.ncopy) * pl.copy_stride_pairs;
-        const uint32_t NEID = (uint32_t)L + 3u;
-        const int YX = G2 + R, RA4 = pl.RA4;
-        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
-        const int NQ_A = pl.NQ_A, NQ_BO = pl.NQ_BO, NQ_BS = pl.NQ_BS, NQ_D = (kw > 1) ? pl.NQ_D : 0;
-        const bool roleZ = warp == 0 || warp == 5, roleX = warp == 1, roleS = warp == 2, roleT = warp == 3 || warp == 4;
-        const int zidx = warp == 0 ? 0 : 1;                   // which of the two gate warps
-        const int EO = efor(O);
-        float v[EK][BT];
-        float sacc[2][NV];                                    // skip accumulators of the skip warp (<= 2 quads)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int i = 0; i < NV; ++i) sacc[q][i] = 0.f;
-        // landing buffer + mbarrier of this warp (gate warps: (y;x); residual and skip warps: y or a head vector)
-        uint2* land_base = reinterpret_cast<uint2*>(sm + pl.sm_land);
-        uint64_t* land_bar0 = reinterpret_cast<uint64_t*>(land_base + 2 * pl.land_z_pairs + 2 * pl.land_y_pairs);
-        const int lslot = warp == 0 ? 0 : (warp == 5 ? 1 : (warp == 1 ? 2 : 3));
-        uint2* land = land_base + (lslot < 2 ? lslot * pl.land_z_pairs : 2 * pl.land_z_pairs + (lslot - 2) * pl.land_y_pairs);
-        uint64_t* lbar = land_bar0 + lslot;
-        uint32_t lph = 0;
-        int nstash = 0;                                       // stashes written (warp 0) / consumed (warps 2-4)
-        const bool prof = (pp.prof != nullptr) && tid == 0;
-        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+    // --------------------------------------------------------------------------------------
+    // deferred group (warps 4-7): queued older-tap products and skip rows, one stage behind
+    // --------------------------------------------------------------------------------------
+    __device__ void def_loop() {
+        const int L = pl.L, R = pl.R, G2 = pl.G2, T = pp.T, P = pl.P, kw = pl.kw;
+        int s0, ns;
+        wn_part(pl.S, P, p, s0, ns);
+        const int NQ_D = pl.NQ_D, NQ_BS = pl.NQ_BS, nqd = (kw > 1 ? NQ_D : 0) + NQ_BS;
+        const int qoff = (kw > 1 ? NQ_D : 0);
+        const int nring_items = (kw - 1) * pl.RA * BT, nskip_items = ns * BT;
+        float xr[ER][BT], yr[EG][BT];
+        const bool prof = (pp.prof != nullptr) && gt == 0;
+        long long pc[4] = {0, 0, 0, 0}, tc = 0;
 #define WN_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
+        int nstash = 0;
 
-        if (warp >= WN_GW) build_pre(0, WN_NTC, WN_NT - WN_NTC);
+        // one deferred stage: `Td` = older taps of `layer` (uses x), `Sk`/`skb` = skip rows of `layer`
+        // (uses y; nullptr in the tail stage, where the critical group evaluates them itself)
+        auto stage = [&](int t, int s, int layer, const float* Td, const float* Sk, const float* skb) {
+            wait_count<true>(s_stash_cnt, nstash + 1, 0x04000000u);
+            ++nstash;
+            WN_TICK(0);
+            unstash<ER>(xs + (size_t)(s & 1) * R * BT, R, xr);
+            if (Sk) unstash<EG>(ys + (size_t)(s & 1) * G2 * BT, G2, yr);
+            float* red = red2 + (size_t)(s & 1) * pl.red2_floats;
+            const int nq = Sk ? nqd : qoff;
+            for (int q = 0; q < nq; q += NA) {
+                float acc[NA][NV];
+#pragma unroll
+                for (int h = 0; h < NA; ++h) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[h][v] = 0.f;
+                    const int qq = q + h;
+                    if (qq < qoff) quad_fma<ER>(Td + (size_t)qq * R * 4, R, xr, acc[h]);
+                    else if (qq < nq) quad_fma<EG>(Sk + (size_t)(qq - qoff) * G2 * 4, G2, yr, acc[h]);
+                }
+                reduce_scatter_multi<NA, NV>(acc, lane);
+#pragma unroll
+                for (int h = 0; h < NA; ++h)
+                    if (q + h < nq) quad_store(acc[h], q + h, red);
+            }
+            WN_TICK(1);
+            const bool d = bar_or_n<2, WN_NTC>(dead);
+            if (!d) {
+                // older-tap products of `layer` -> history ring (consumed at steps t+d, t+2d, conv.py:32-44)
+                for (int f = gt; f < nring_items; f += WN_NTC) {
+                    const int dr = f / BT, db = f % BT, tap = dr / pl.RA, rr = dr % pl.RA;
+                    const int e = (layer * (kw - 1) + tap) * 3;
+                    ring[((size_t)ringtab[e] + ringtab[e + 2]) * pl.RA4 * BT + rr * BT + db] = red_sum(red, dr, db);
+                }
+                // skip rows, accumulated in layer order (wavenet.py:312)
+                if (Sk) {
+                    for (int f = gt; f < nskip_items; f += WN_NTC) {
+                        const int fr = f / BT, fb = f % BT;
+                        const float h = red_sum(red, qoff * 4 + fr, fb) + skb[fr];
+                        skipacc[f] = (layer == 0) ? h : skipacc[f] + h;
+                    }
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd((int*)s_ddone_cnt, 1);
+            WN_TICK(2);
+            return d;
+        };
+
+        build_pre(0);
         if (bar_or_n<3, WN_NT>(dead)) return;
-
         for (int t = 0; t < T; ++t) {
-            const uint32_t tagbase = (uint32_t)t * NEID + 1u;
             if (prof) tc = clock64();
-            // ================================================================ gate warps
-            if (roleZ) {
-                const bool zwork = (warp == 0) || (zidx < NQ_A);
-                for (int s = 0; s < L && !dead; ++s) {
-                    if (!zwork) { acquire_blob(t, s); release_blob(t, s); continue; }   // never run ahead of the ring
-                    const float* W = acquire_blob(t, s);
-                    const uint32_t tag_in = tagbase + wn_eid_yx(s - 1), tag_out = tagbase + wn_eid_yx(s);
-                    const int e_in = pl.ex_yx + (s - 1) * YX;
-                    WN_TICK(4);
-                    if (s == 0) make_x0(v);
-                    else if (s == 1) { tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v); make_x0(v); }     // x_0 is known locally
-                    else tpoll(land, lbar, lph, xin, e_in, YX, tag_in, v);
-                    WN_TICK(0);
-                    for (int q = zidx; q < NQ_A; q += 2) {
-                        float acc[NV];
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                        if (s == 0) wfma(W + pl.fb_Zx + (size_t)q * R * 4, G2, R, v, acc);
-                        else wfma(W + pl.lb_Zy + (size_t)q * YX * 4, 0, YX, v, acc);     // [M_{s-1} | V_s] rows over (y ; x)
-                        reduce_scatter<NV>(acc, lane);
-                        // rows of the quad are a_j, b_j, a_{j+1}, b_{j+1}: the b row sits BT values (8 lanes) further
-                        const float other = __shfl_down_sync(0xffffffffu, acc[0], BT * LPV);
-                        const int r = my_row(), b = my_b(), j = 2 * q + (r >> 1);
-                        if (holds_value() && (r & 1) == 0 && j < ny) {
-                            const float* pr = pre + ((size_t)s * RA4 + 4 * q + r) * BT + b;
-                            publish(pl.ex_yx + s * YX + y0 + j, b, 0, gate(acc[0] + pr[0], other + pr[BT]), tag_out);
-                        }
-                    }
-                    WN_TICK(1);
-                    if (warp == 0 && s >= 1) {
-                        // hand (y_{s-1}, x_{s-1}) to the skip / older-tap warps; the buffer of stage s-2 must be free
-                        wait_count<true>(s_ddone_cnt, 3 * (nstash - 1), 0x08000000u);
-                        float* st = xs + (size_t)(s & 1) * YX * BT;
-#pragma unroll
-                        for (int j = 0; j < EK; ++j) {
-                            const int e = lane + 32 * j;
-                            if (e < YX) {
-#pragma unroll
-                                for (int b = 0; b < BT; ++b) st[e * BT + b] = v[j][b];
-                            }
-                        }
-                        __threadfence_block();
-                        __syncwarp();
-                        ++nstash;
-                        if (lane == 0) *s_stash_cnt = nstash;
-                    }
-                    release_blob(t, s);
-                    WN_TICK(3);
-                }
-                // stage L: warp 0 only forwards x_{L-1} to the older-tap warps
-                if (warp == 0 && !dead) {
-                    if (L == 1) { tpoll(land, lbar, lph, xin, pl.ex_yx, G2, tagbase + wn_eid_yx(0), v); make_x0(v); }
-                    else tpoll(land, lbar, lph, xin, pl.ex_yx + (L - 1) * YX, YX, tagbase + wn_eid_yx(L - 1), v);
-                    wait_count<true>(s_ddone_cnt, 3 * (nstash - 1), 0x08000001u);
-                    float* st = xs + (size_t)(L & 1) * YX * BT;
-#pragma unroll
-                    for (int j = 0; j < EK; ++j) {
-                        const int e = lane + 32 * j;
-                        if (e < YX) {
-#pragma unroll
-                            for (int b = 0; b < BT; ++b) st[e * BT + b] = v[j][b];
-                        }
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    ++nstash;
-                    if (lane == 0) *s_stash_cnt = nstash;
-                }
+            bool step_dead = false;
+            release_blob(t, 0);                       // stage 0 has no deferred work
+            for (int s = 1; s < L && !step_dead; ++s) {
+                const float* W = acquire_blob(t, s);
+                step_dead = stage(t, s, s - 1, W + pl.lb_Td, W + pl.lb_Sk, W + pl.lb_sb);
+                release_blob(t, s);
             }
-            // ================================================================ residual warps
-            if (roleX) {
-                acquire_blob(t, 0);
-                release_blob(t, 0);
-                for (int s = 1; s < L && !dead; ++s) {
-                    const float* W = acquire_blob(t, s);
-                    for (int q = 0; q < NQ_BO; ++q) {
-                        // x_s rows of this quad: conv1x1_out(y_{s-1}) + x_{s-1}  (modules.py:160-162)
-                        const int r = my_row(), b = my_b(), row = 4 * q + r;
-                        const bool fin = holds_value() && row < nx;
-                        float xprev = 0.f;
-                        const int e_in = pl.ex_yx + (s - 1) * YX;
-                        const uint32_t tag_in = tagbase + wn_eid_yx(s - 1);
-                        if (s >= 2) tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v, fin ? e_in + G2 + x0r + row : e_in, fin ? b : 0, &xprev);
-                        else {
-                            tpoll(land, lbar, lph, xin, e_in, G2, tag_in, v);
-                            if (fin) {
-                                const int k = x0r + row;      // x_0 rows are computed locally
-                                if (pl.input_kind == 0) xprev = fmaf(first[k], s_in[b], first[R + k]);
-                                else {
-                                    const int idx = s_idx[b];
-                                    if (idx >= 0) xprev = __ldg(pp.first_w + (size_t)idx * R + k) + first[R + k];
-                                    else {
-                                        float a = 0.f;
-                                        for (int o = 0; o < O; ++o)
-                                            a = fmaf(__ldg(pp.first_w + (size_t)o * R + k), s_dense[b * O + o], a);
-                                        xprev = a + first[R + k];
-                                    }
-                                }
-                            }
-                        }
-                        float acc[NV];
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                        wfma(W + pl.lb_Xo + (size_t)q * G2 * 4, 0, G2, v, acc);
-                        reduce_scatter<NV>(acc, lane);
-                        if (fin)
-                            publish(pl.ex_yx + s * YX + G2 + x0r + row, b, 0,
-                                    (acc[0] + W[pl.lb_xb + row] + xprev) * RSQRT2, tagbase + wn_eid_yx(s));
-                    }
-                    release_blob(t, s);
-                }
-            }
-            // ================================================================ skip warp and older-tap warps
-            if (roleS || roleT) {
-                acquire_blob(t, 0);
-                release_blob(t, 0);
-                for (int s = 1; s <= L && !dead; ++s) {
-                    const bool tail = (s == L);
-                    const float* W = acquire_blob(t, s);     // (idempotent: a second acquire of the same blob just re-tests its barrier)
-                    const int layer = s - 1;
-                    if (roleS && tail) {
-                        // the last layer's skip rows are on the critical path: read y_{L-1} straight from L2
-                        tpoll(land, lbar, lph, xin, pl.ex_yx + (L - 1) * YX, G2, tagbase + wn_eid_yx(L - 1), v);
-                        ++nstash;
-                    } else {
-                        wait_count<true>(s_stash_cnt, nstash + 1, 0x04000000u);
-                        ++nstash;
-                        const float* st = xs + (size_t)(s & 1) * YX * BT;
-                        const int e0 = roleS ? 0 : G2, K = roleS ? G2 : R;
-#pragma unroll
-                        for (int j = 0; j < EK; ++j) {
-                            const int e = lane + 32 * j;
-                            if (e < K) {
-#pragma unroll
-                                for (int b = 0; b < BT; ++b) v[j][b] = st[(e0 + e) * BT + b];
-                            }
-                        }
-                    }
-                    if (roleS) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            if (q < NQ_BS) {
-                                float acc[NV];
-#pragma unroll
-                                for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                                wfma(W + (tail ? pl.tb_Sk : pl.lb_Sk) + (size_t)q * G2 * 4, 0, G2, v, acc);
-                                reduce_scatter<NV>(acc, lane);
-                                const int row = 4 * q + my_row();
-                                // skip rows accumulate in layer order (wavenet.py:312); the running sum lives in registers
-                                const float h = acc[0] + W[(tail ? pl.tb_sb : pl.lb_sb) + (row < pl.NSm ? row : 0)];
-                                sacc[q][0] = (layer == 0) ? h : sacc[q][0] + h;
-                                if (tail && holds_value() && row < ns)
-                                    publish(pl.ex_sk + s0 + row, my_b(), 0, fmaxf(sacc[q][0] * pl.skip_scale, 0.f),
-                                            tagbase + wn_eid_sk(pl));          // * sqrt(1/L), first ReLU (wavenet.py:313-315)
-                            }
-                        }
-                    } else {
-                        const float* Td = W + (tail ? pl.tb_Td : pl.lb_Td);
-                        for (int q = warp - 3; q < NQ_D; q += 2) {
-                            float acc[NV];
-#pragma unroll
-                            for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                            wfma(Td + (size_t)q * R * 4, 0, R, v, acc);
-                            reduce_scatter<NV>(acc, lane);
-                            // queue the older taps' products of `layer` (consumed at t+d, t+2d; conv.py:32-44)
-                            const int rowidx = 4 * q + my_row();
-                            if (holds_value() && rowidx < (kw - 1) * pl.RA) {
-                                const int tap = rowidx / pl.RA, rr = rowidx % pl.RA, e = (layer * (kw - 1) + tap) * 3;
-                                ring[((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT + rr * BT + my_b()] = acc[0];
-                            }
-                        }
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd((int*)s_ddone_cnt, 1);
-                    if (!tail) release_blob(t, s);
-                }
-            }
-            // ================================================================ head (wavenet.py:315-319), warps 0-3
-            if (warp < WN_GW && !dead) {
+            if (!step_dead) {
                 const float* H = acquire_blob(t, L);
-                const int hslot = warp < 3 ? warp : 99;     // warps 0, 1, 2 own a landing buffer
-                for (int q = hslot; q < pl.NQ_HA; q += 3) {
-                    tpoll(land, lbar, lph, xin, pl.ex_sk, S, tagbase + wn_eid_sk(pl), v);
-                    float acc[NV];
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                    wfma(H + pl.tb_Ha + (size_t)q * S * 4, 0, S, v, acc);
-                    reduce_scatter<NV>(acc, lane);
-                    const int row = 4 * q + my_row();
-                    if (holds_value() && row < na)
-                        publish(pl.ex_h1 + a0 + row, my_b(), 0, fmaxf(acc[0] + H[pl.tb_Hab + row], 0.f), tagbase + wn_eid_h1(pl));
-                }
-                for (int q = hslot; q < pl.NQ_HB; q += 3) {
-                    if (4 * q >= nb) break;
-                    tpoll(land, lbar, lph, xin, pl.ex_h1, S, tagbase + wn_eid_h1(pl), v);
-                    float acc[NV];
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-                    wfma(H + pl.tb_Hb + (size_t)q * S * 4, 0, S, v, acc);
-                    reduce_scatter<NV>(acc, lane);
-                    const int row = 4 * q + my_row();
-                    if (holds_value() && row < nb)
-                        publish(pl.ex_h2 + b0 + row, my_b(), 0, acc[0] + H[pl.tb_Hbb + row], tagbase + wn_eid_h2(pl));
-                }
-                WN_TICK(5);
-                // head outputs for the sampler (all four warps share the read)
-                WN_DISPATCH_E(EO, { float h[E][BT];
-                                    poll_vec<E>(xin, pl.ex_h2, O, tagbase + wn_eid_h2(pl), h);
-                                    stash<E>(hs, O, h); });
-                WN_TICK(0);
+                step_dead = stage(t, L, L - 1, H + pl.tb_Td, nullptr, nullptr);
+                release_blob(t, L);
             }
-            if (warp == 5) acquire_blob(t, L);
-            release_blob(t, L);
-            if (step_end(t, false)) return;
-            WN_TICK(6);
+            if (!step_dead && t + 1 < T) {
+                // all rings of step t are written (group barrier inside stage()): pre-sums of step t+1
+                if (bar_or_n<2, WN_NTC>(dead)) step_dead = true;
+                else build_pre(t + 1);
+            }
+            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            step_tail(t);
+            if (bar_or_n<3, WN_NT>(false)) return;
+            WN_TICK(3);
         }
         if (prof) {
-            for (int i = 0; i < 8; ++i) pp.prof[(size_t)p * 16 + i] = pc[i];
+            for (int i = 0; i < 4; ++i) pp.prof[(size_t)p * 16 + 8 + i] = pc[i];
         }
 #undef WN_TICK
     }
@@ -1138,11 +1205,11 @@ struct Engine {
 // ------------------------------------------------------------------------------------------
 // kernel entry
 // ------------------------------------------------------------------------------------------
-template <int BT, int EK>
+template <int BT, int ER, int EG>
 __global__ void __launch_bounds__(WN_NTHREADS, 1)
 wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ WnPtrs pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Engine<BT, EK> eng(pl, pp, smem_raw);
+    Engine<BT, ER, EG> eng(pl, pp, smem_raw);
     const int tid = threadIdx.x, p = blockIdx.x;
     const int nslots = pl.nres + pl.nring;
     if (tid == 0) {
@@ -1150,11 +1217,7 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         for (int i = 0; i < pl.nring; ++i) mbar_init(&eng.bar_empty[i], WN_NWARP);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&eng.bar_cfull[i], 1);
-            mbar_init(&eng.bar_cempty[i], WN_NWARP - WN_GW);     // the warps that build the pre-sum table
-        }
-        {
-            uint64_t* lb = reinterpret_cast<uint64_t*>(reinterpret_cast<uint2*>(smem_raw + pl.sm_land) + 2 * pl.land_z_pairs + 2 * pl.land_y_pairs);
-            for (int i = 0; i < 4; ++i) mbar_init(lb + i, 1);
+            mbar_init(&eng.bar_cempty[i], WN_GW);
         }
         *eng.s_abort = 0;
         *eng.s_stash_cnt = 0;
@@ -1230,7 +1293,8 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
         if (pl.C > 0) eng.cond_loop();
         return;
     }
-    eng.compute_loop();
+    if (warp < WN_GW) eng.crit_loop();
+    else eng.def_loop();
 }
 
 // gbias[b][l][row] = Wg_l[row,:] . g_b   (modules.py:148-152), once per call
