@@ -135,8 +135,10 @@ def ncu_traffic(T, U):
     try:
         with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
             d = json.load(f)
-        if d.get("T") == T and d.get("utts_per_gpu") == U:
-            return d["dram_bytes_per_launch"]
+        if d.get("utts_per_gpu") == U:
+            # the full-set capture is taken at a shorter T (ncu replays the launch ~40 times); DRAM traffic
+            # is proportional to the number of generated samples, so scale to this launch
+            return d["dram_bytes_per_sample"] * T
     except Exception:
         pass
     return None
