@@ -200,12 +200,6 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         pl.sm_noise = take((long long)BT * (pl.O + 2) * 4, 16);
         pl.sm_first = take(2LL * pl.R * 4, 16);
         pl.sm_ring = take(ring_smem ? ring_bytes : 16, 16);
-        {
-            // landing area of the asynchronous exchange copies: 128 threads x chunks(16 B) per thread
-            auto ef = [](int K) { return K <= 128 ? 1 : (K <= 256 ? 2 : (K <= 512 ? 4 : 8)); };
-            const int chunks = ((ef(pl.R) + ef(pl.G2)) * BT + 1) / 2 + ((std::max(ef(pl.S), ef(pl.O)) * BT + 1) / 2);
-            pl.sm_land = take((long long)chunks * 128 * 16, 128);
-        }
         pl.sm_slots = take(0, 128);
         return off;
     };

@@ -134,15 +134,6 @@ __device__ __forceinline__ uint4 ld_pair2(const uint2* p) {
                  : "memory");
     return v;
 }
-// Ampere-style asynchronous 16-byte copy global -> shared through L2 (.cg: never L1).  Unlike the
-// L1-bypassing loads above, which cost the issuing warp ~250 cycles EACH and do not overlap, any number of
-// these can be in flight per thread (SASS: LDGSTS); completion is awaited with cp.async.wait_group.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 __device__ __forceinline__ void st_pair(uint2* p, float v, uint32_t tag) {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
                  : "memory");
@@ -391,63 +382,48 @@ struct Engine {
         if constexpr (BT == 1 && (E % 2) == 0) return 2 * gt + 2 * WN_NTC * (j >> 1) + (j & 1);
         else return gt + j * WN_NTC;
     }
-    // One attempt to read the thread's share of a broadcast vector.  `src` is the base of the block's replica,
-    // `e0` the first element of the vector, `c0` the first 16-byte chunk of the thread's landing area to use
-    // (chunk c of thread gt lives at land[c*128 + gt]: conflict-free 16-byte shared accesses).
+    // `src` is the base of the block's replica, `e0` the first element of the vector
     template <int E>
     __device__ __forceinline__ uint32_t load_vec(const uint2* __restrict__ src, int e0, int K, uint32_t tag,
-                                                 float (&x)[E][BT], int c0 = 0) {
+                                                 float (&x)[E][BT]) {
         uint32_t bad = 0;
-        uint4* land = reinterpret_cast<uint4*>(sm + pl.sm_land);
         if constexpr (BT == 1 && (E % 2) == 0) {
+            uint4 raw[E / 2];
 #pragma unroll
             for (int j = 0; j < E / 2; ++j) {
                 const int k = elem<E>(2 * j);
-                if (k < K) cp_async16(&land[(c0 + j) * WN_NTC + gt], src + wn_pair_index((long long)(e0 + k)));
+                raw[j] = make_uint4(0u, tag, 0u, tag);
+                if (k < K) raw[j] = ld_pair2(src + wn_pair_index((long long)(e0 + k)));
             }
-            cp_async_wait_all();
 #pragma unroll
             for (int j = 0; j < E / 2; ++j) {
-                const int k = elem<E>(2 * j);
-                uint4 raw = make_uint4(0u, tag, 0u, tag);
-                if (k < K) raw = land[(c0 + j) * WN_NTC + gt];
-                bad |= (raw.y ^ tag) | ((k + 1 < K) ? (raw.w ^ tag) : 0u);
-                x[2 * j][0] = __uint_as_float(raw.x);
-                x[2 * j + 1][0] = __uint_as_float(raw.z);
-            }
-        } else if constexpr (BT >= 2) {
-#pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const int k = elem<E>(j);
-                if (k < K) {
-#pragma unroll
-                    for (int b = 0; b < BT / 2; ++b)
-                        cp_async16(&land[(c0 + j * (BT / 2) + b) * WN_NTC + gt],
-                                   src + wn_pair_index((long long)(e0 + k) * BT) + 2 * b);
-                }
-            }
-            cp_async_wait_all();
-#pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const int k = elem<E>(j);
-#pragma unroll
-                for (int b = 0; b < BT / 2; ++b) {
-                    uint4 raw = make_uint4(0u, tag, 0u, tag);
-                    if (k < K) raw = land[(c0 + j * (BT / 2) + b) * WN_NTC + gt];
-                    bad |= (raw.y ^ tag) | (raw.w ^ tag);
-                    x[j][2 * b] = __uint_as_float(raw.x);
-                    x[j][2 * b + 1] = __uint_as_float(raw.z);
-                }
+                bad |= (raw[j].y ^ tag) | ((elem<E>(2 * j) + 1 < K) ? (raw[j].w ^ tag) : 0u);
+                x[2 * j][0] = __uint_as_float(raw[j].x);
+                x[2 * j + 1][0] = __uint_as_float(raw[j].z);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < E; ++j) {
                 const int k = elem<E>(j);
-                x[j][0] = 0.f;
                 if (k < K) {
-                    const uint2 v = ld_pair(src + wn_pair_index((long long)(e0 + k)));
-                    x[j][0] = __uint_as_float(v.x);
-                    bad |= v.y ^ tag;
+                    const uint2* s = src + wn_pair_index((long long)(e0 + k) * BT);
+                    if constexpr (BT == 1) {
+                        const uint2 v = ld_pair(s);
+                        x[j][0] = __uint_as_float(v.x);
+                        bad |= v.y ^ tag;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < BT; b += 2) {
+                            const uint4 v = ld_pair2(s + b);
+                            x[j][b] = __uint_as_float(v.x);
+                            bad |= v.y ^ tag;
+                            x[j][b + 1] = __uint_as_float(v.z);
+                            bad |= v.w ^ tag;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) x[j][b] = 0.f;
                 }
             }
         }
@@ -472,7 +448,7 @@ struct Engine {
         uint32_t spins = 0;
         long long t0 = 0;
         while (true) {
-            const uint32_t bad = load_vec<EA>(src, ea, KA, tag, a, 0) | load_vec<EB>(src, eb, KB, tag, b, (EA * BT + 1) / 2);
+            const uint32_t bad = load_vec<EA>(src, ea, KA, tag, a) | load_vec<EB>(src, eb, KB, tag, b);
             if (bad == 0) return;
             if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                 dead = true;

@@ -77,7 +77,7 @@ struct WnPlan {
     int RA4;                    // 4*NQ_A
     // ---- shared memory map (byte offsets)
     int sm_bar, sm_misc, sm_ringtab, sm_xs, sm_red1, sm_red2, sm_sb, sm_cond, sm_skipacc, sm_hs,
-        sm_noise, sm_in, sm_first, sm_ring, sm_land, sm_slots, smem_bytes;
+        sm_noise, sm_in, sm_first, sm_ring, sm_slots, smem_bytes;
     int red1_floats;            // one of the two critical-partials buffers (alternating by stage)
     int red2_floats;            // one of the two deferred-partials buffers
     float skip_scale;           // sqrt(1/L), wavenet.py:313
