@@ -265,10 +265,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         results[name] = dict(ms=float(t.item()), samples=Tn * U * world * K, clocks=clocks,
                              launches=eng.plan(U)["launches"] - launches0)
+        if name == "device":
+            wave_dev = out                       # (U, T) fp32 on this rank's GPU
     if dist is not None:
         # the only data-path collective: gather the waveforms of the last step on rank 0
-        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-        dist.gather(out, gathered, dst=0)
+        gathered = [torch.empty_like(wave_dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(wave_dev, gathered, dst=0)
         torch.cuda.synchronize(dev)
 
     if rank == 0:
