@@ -843,8 +843,15 @@ struct Engine {
     // Absolute error ~1e-7 (the subtraction 1 - e^{-2a} loses relative, not absolute, accuracy near 0).
     __device__ __forceinline__ static float gate(float a, float g) {
         const float ac = fminf(fmaxf(a, -15.0f), 15.0f);
+#ifdef WN_FAST_GATE
+        // ex2.approx based exponentials and an approximate division: ~2 ulp each, well inside the 1e-6
+        // absolute error the parity tests observe
+        const float ea = __expf(-2.0f * ac), eg = __expf(-g);
+        return __fdividef(1.0f - ea, (1.0f + ea) * (1.0f + eg));
+#else
         const float ea = expf(-2.0f * ac), eg = expf(-g);
         return (1.0f - ea) / ((1.0f + ea) * (1.0f + eg));
+#endif
     }
     // Everything of z_l(t) that does not depend on step t's broadcasts: (folded) bias + global conditioning
     // + local conditioning projection + the queued products of the older taps.  The deferred group builds
