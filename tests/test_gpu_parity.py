@@ -329,3 +329,49 @@ def test_config2_full_length_properties():
     # philox streams are keyed by (seed, step, utterance index): row 0 alone must match row 0 of the batch
     y0 = mc.incremental_forward(c=c[:1, :, :Ts], T=Ts, seed=77)
     assert float((yb[:1] - y0).abs().max()) <= 1e-4
+
+
+def test_c_abi_host_buffer_entry():
+    """wn_generate_host: the same call with HOST buffers everywhere (copies inside, synchronous).
+    Driven through ctypes exactly as INTEGRATION.md shows; checked against the golden vectors."""
+    import ctypes as C
+    from wavenet_vocoder_b200 import _native as N
+    from wavenet_vocoder_b200.engine import make_config, weights_struct
+    gc = GoldenCase("mol_cond")
+    kw = gc.kw
+    cfg = make_config(layers=kw["layers"], stacks=kw["stacks"], residual_channels=kw["residual_channels"],
+                      gate_channels=kw["gate_channels"], skip_out_channels=kw["skip_out_channels"],
+                      out_channels=kw["out_channels"], kernel_size=3, cin_channels=kw["cin_channels"],
+                      gin_channels=-1, scalar_input=True, output_distribution="Logistic", device_index=0)
+    h = C.c_void_p()
+    N.check(N.lib().wn_create(C.byref(cfg), C.byref(h)))
+    try:
+        w, keep = weights_struct(gc.sd, cfg.layers, cfg.cin_channels, 0)
+        N.check(N.lib().wn_load_weights(h, C.byref(w)))
+        B, T, K = gc.B, gc.T, kw["out_channels"] // 3
+        c = np.ascontiguousarray(gc.arr["c_up"].transpose(0, 2, 1)).astype(np.float32)       # (B,T,C)
+        x_tf = np.ascontiguousarray(gc.arr["x_tf"].reshape(B, T)).astype(np.float32)
+        u1 = np.ascontiguousarray(gc.noise_tf["u1"].numpy())
+        u2 = np.ascontiguousarray(gc.noise_tf["u2"].numpy())
+        out = np.zeros((B, T), np.float32)
+        params = np.zeros((B, kw["out_channels"], T), np.float32)
+        a = N.wn_generate_args()
+        a.B, a.T, a.T_test = B, T, T
+        a.c = c.ctypes.data
+        a.test_scalar = x_tf.ctypes.data
+        a.flags = N.WN_FLAG_SOFTMAX | N.WN_FLAG_QUANTIZE
+        a.noise_kind = N.WN_NOISE_REPLAY
+        a.noise_u1, a.noise_u2 = u1.ctypes.data, u2.ctypes.data
+        a.out_scalar, a.params_out = out.ctypes.data, params.ctypes.data
+        N.check(N.lib().wn_generate_host(h, C.byref(a)))
+        assert float(np.abs(params - gc.arr["params_tf"]).max()) <= PARAM_TOL
+        assert float(np.abs(out - gc.arr["y_tf"].reshape(B, T)).max()) <= 1e-4
+        # argument errors come back as status codes with a message, not crashes
+        a.c = None
+        assert N.lib().wn_generate_host(h, C.byref(a)) == -1
+        assert b"c is required" in N.lib().wn_last_error()
+        info = N.wn_plan_info()
+        N.check(N.lib().wn_get_plan(h, 1, C.byref(info)))
+        assert info.launches >= 1 and info.exchanges_per_step == cfg.layers + 3
+    finally:
+        N.lib().wn_destroy(h)

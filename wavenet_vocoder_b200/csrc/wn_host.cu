@@ -432,6 +432,8 @@ struct WnHandle {
     bool pending = false;
     int64_t launches = 0;
     bool attr_set[16] = {};
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 carve-out for the packed weights
+    size_t wpack_bytes = 0;
 };
 
 template <typename T>
@@ -548,7 +550,30 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     }
     // cooperative launch: the runtime refuses to start unless all P blocks are co-resident,
     // which the spin-wait exchanges require
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(pl.P), dim3(WN_NTHREADS), kargs, (size_t)pl.smem_bytes, st));
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(pl.P);
+    lc.blockDim = dim3(WN_NTHREADS);
+    lc.dynamicSmemBytes = (size_t)pl.smem_bytes;
+    lc.stream = st;
+    cudaLaunchAttribute la[2];
+    int na = 0;
+    la[na].id = cudaLaunchAttributeCooperative;
+    la[na].val.cooperative = 1;
+    ++na;
+    if (h->l2_persist_bytes > 0 && h->wpack_bytes > 0) {
+        const size_t win = std::min(h->wpack_bytes, h->l2_window_max);
+        la[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        la[na].val.accessPolicyWindow.base_ptr = (void*)h->d_wpack;
+        la[na].val.accessPolicyWindow.num_bytes = win;
+        la[na].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_bytes / (double)win);
+        la[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        la[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    }
+    lc.attrs = la;
+    lc.numAttrs = na;
+    CUDA_TRY(cudaLaunchKernelExC(&lc, fn, kargs));
     h->launches++;
     return WN_OK;
 }
@@ -616,6 +641,17 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
         delete h;
         return rc;
     }
+    if (env_int("WN_L2_PERSIST", 0) && prop.persistingL2CacheMaxSize > 0) {
+        // Optional (WN_L2_PERSIST=1): pin as much of the packed weight image as allowed in the persisting part of
+        // the 126 MB L2.  The cyclic 112 MB/sample stream otherwise evicts itself (ncu: 16 % hit rate), but the
+        // weights are not on the critical path: measured 44.7 us/sample with the window vs 44.1 without, so off.
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+            h->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+            h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else {
+            cudaGetLastError();
+        }
+    }
     h->cfg.num_ctas = h->base.P;          // freeze the partition so every batch tile agrees with the packing
     h->cfg.exchange_copies = h->base.ncopy;
     if (cudaMalloc((void**)&h->d_err, 16) != cudaSuccess || cudaMemset(h->d_err, 0, 16) != cudaSuccess) {
@@ -661,6 +697,7 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
         for (int p = 0; p < pl.P; ++p) pack_cta(pl, *w, fo, p, img.data() + (size_t)p * pl.cta_w_floats);
     }
     if ((rc = upload(&h->d_wpack, img))) return rc;
+    h->wpack_bytes = img.size() * sizeof(float);
     std::vector<float> cw((size_t)pl.P * pl.cta_cw_floats);
     for (int p = 0; p < pl.P; ++p) pack_cw_cta(pl, *w, p, cw.data() + (size_t)p * pl.cta_cw_floats);
     if ((rc = upload(&h->d_cwpack, cw))) return rc;
