@@ -31,14 +31,20 @@
 //       group and does everything that is only needed later (queued older-tap products, skip rows).
 // plus one warp that streams weights (TMA) and one that projects the local conditioning.
 //
-// Exchange protocol: every value travels as an 8-byte (value, tag) pair (tag = step*NE+id+1),
-// written with one 8-byte store and polled with 8/16-byte loads, so data and "ready" flag are
-// one atomic word: no fences, no separate barrier, one L2 write + one L2 read per hop.  Measured on
-// B200 (profiles/r1_xbench_l2_broadcast.txt): P=128 blocks reading the same lines serialise at the L2
-// slice (~10 cycles per same-line request, ~1650 cycles per round even when the data is already
-// there), and one thread writing several replicas pays ~100-190 cycles per st.relaxed.gpu.  So every
-// vector has `ncopy` replicas, each replica is written by a DIFFERENT thread (the finalizer work is
-// simply done `ncopy` times in parallel), and block p reads replica p % ncopy.
+// Exchange protocol: every value travels as an 8-byte (value, tag) pair (tag = step*NE+id+1), written with
+// one 8-byte store and polled with 8/16-byte loads, so data and "ready" flag are one atomic word: no
+// fences, no separate barrier, one L2 write + one L2 read per hop.  What round 1 measured on B200 and the
+// code is shaped by (logs under profiles/):
+//   * an L1-bypassing coherent load (SASS LDG.E.64/128.STRONG.GPU) costs the issuing warp ~250 cycles and
+//     several of them from one warp do not overlap, however they are scheduled -> the poll time is
+//     (loads per thread) x 250 cycles: the vector is read by the 128 threads of the critical group, and with
+//     one utterance per launch each thread owns PAIRS of adjacent elements fetched by one 16-byte load
+//     (3 loads per thread for config 2);  one-warp-per-quad polling (24 loads per lane), TMA bulk-copy
+//     polling and cp.async polling were all measured slower;
+//   * a thread that writes several replicas of its value pays ~100-190 cycles per st.relaxed.gpu, and
+//     replicas written by different threads still cost more in scattered stores than they save: one copy
+//     (`ncopy` = 1; the replica mechanism is kept for experiments);
+//   * spreading the pairs over more L2 slices (wn_pair_index) makes no measurable difference.
 //
 // Weights: fp32, packed per block by the host ("blobs").  A dedicated warp streams the blobs
 // into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a ring
