@@ -375,3 +375,76 @@ def test_c_abi_host_buffer_entry():
         assert info.launches >= 1 and info.exchanges_per_step == cfg.layers + 3
     finally:
         N.lib().wn_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own online == offline tests (tests/test_model.py:147-366 there: teacher-forced
+# incremental_forward vs the batch forward(), atol 1e-4, warn-only) restated with synthetic inputs and
+# a hard assert.  The batch side runs on a CPU copy of the module (plain fp32 PyTorch).
+# ------------------------------------------------------------------------------------------------
+ONLINE_OFFLINE = {
+    "incremental_forward_correctness": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32,
+                                                    gate_channels=32, skip_out_channels=32, scalar_input=False)),
+    "local_conditioning": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32, gate_channels=32,
+                                       skip_out_channels=32, cin_channels=2, scalar_input=False), c="sample"),
+    "local_conditioning_upsample": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32,
+                                                gate_channels=32, skip_out_channels=32, cin_channels=2,
+                                                scalar_input=False, upsample_conditional_features=True,
+                                                upsample_params={"upsample_scales": [2, 2], "cin_channels": 2}),
+                                        c="frames"),
+    "global_conditioning_with_embedding": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32,
+                                                       gate_channels=32, skip_out_channels=32, gin_channels=16,
+                                                       n_speakers=4, use_speaker_embedding=True, scalar_input=False),
+                                               g="ids"),
+    "global_conditioning_without_embedding": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32,
+                                                          gate_channels=32, skip_out_channels=32, gin_channels=16,
+                                                          use_speaker_embedding=False, scalar_input=False), g="vec"),
+    "global_and_local_conditioning": dict(kw=dict(out_channels=256, layers=4, stacks=2, residual_channels=32,
+                                                  gate_channels=32, skip_out_channels=32, cin_channels=2, gin_channels=16,
+                                                  n_speakers=4, use_speaker_embedding=True, scalar_input=False),
+                                          c="sample", g="ids"),
+    "mixture_wavenet": dict(kw=dict(out_channels=30, layers=4, stacks=2, residual_channels=32, gate_channels=32,
+                                    skip_out_channels=32, cin_channels=1, scalar_input=True), c="sample"),
+}
+
+
+@pytest.mark.parametrize("name", list(ONLINE_OFFLINE))
+def test_online_equals_offline_like_the_reference(name):
+    import copy
+    from wavenet_vocoder_b200 import WaveNet
+    spec = ONLINE_OFFLINE[name]
+    kw = dict(spec["kw"], dropout=0.0)
+    torch.manual_seed(3)
+    cpu = WaveNet(**kw).eval()
+    with torch.no_grad():
+        for n_, p_ in cpu.named_parameters():
+            if n_.endswith(".bias"):
+                p_.normal_(0, 0.05)
+    B, T = 2, 64
+    gen = torch.Generator().manual_seed(8)
+    if kw["scalar_input"]:
+        x = (torch.rand(B, 1, T, generator=gen) * 2 - 1) * 0.9
+    else:
+        idx = torch.randint(0, 256, (B, T), generator=gen)
+        x = torch.zeros(B, 256, T).scatter_(1, idx.unsqueeze(1), 1.0)
+    c = g = None
+    if spec.get("c") == "sample":
+        c = torch.randn(B, kw["cin_channels"], T, generator=gen)
+    elif spec.get("c") == "frames":
+        c = torch.randn(B, kw["cin_channels"], T // 4, generator=gen)
+    if spec.get("g") == "ids":
+        g = torch.randint(0, kw["n_speakers"], (B, 1), generator=gen)
+    elif spec.get("g") == "vec":
+        g = torch.randn(B, kw["gin_channels"], 1, generator=gen)
+    with torch.no_grad():
+        y_offline = cpu(x, c=c, g=g, softmax=False)                               # batch forward
+    gpu = copy.deepcopy(cpu).cuda()
+    if kw["scalar_input"]:
+        y, y_online = gpu.incremental_forward(test_inputs=x, c=c, g=g, T=T, return_params=True)
+        assert y.shape == x.shape                                                 # tests/test_model.py:138,143
+        y_free = gpu.incremental_forward(c=c, g=g, T=T)
+        assert y_free.shape == x.shape
+    else:
+        y_online = gpu.incremental_forward(test_inputs=x, c=c, g=g, T=T, softmax=False, quantize=False)
+    assert y_online.shape == y_offline.shape
+    assert float((y_online.cpu() - y_offline).abs().max()) <= 1e-4                # the reference's own tolerance
