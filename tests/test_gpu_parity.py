@@ -448,3 +448,34 @@ def test_online_equals_offline_like_the_reference(name):
         y_online = gpu.incremental_forward(test_inputs=x, c=c, g=g, T=T, softmax=False, quantize=False)
     assert y_online.shape == y_offline.shape
     assert float((y_online.cpu() - y_offline).abs().max()) <= 1e-4                # the reference's own tolerance
+
+
+def test_initial_input_like_eval_model():
+    """train.eval_model / synthesis.wavegen hand an explicit initial_input: (B,1,1) for scalar models,
+    one-hot (B,1,Q) or (B,Q,1) for mu-law models (train.py:589-602 in the reference)."""
+    gc = GoldenCase("mixgauss")
+    m = cuda_model(gc)
+    T, B = 40, 2
+    noise = orc.predraw_noise(gc.cfg, B, T, 5)
+    init = torch.tensor([[[0.3]], [[-0.6]]])                                       # (B,1,1)
+    y = m.incremental_forward(initial_input=init, T=T, noise=dev_noise(noise))
+    assert y.shape == (B, 1, T)
+    for r in range(B):                                                             # each row against the oracle alone
+        nr = {k: v[:, r:r + 1].contiguous() for k, v in noise.items()}
+        y_ref = orc.incremental_forward(gc.cfg, gc.w, initial_input=init[r:r + 1], T=T,
+                                        noise=orc.replay_from_predrawn(gc.cfg, nr))
+        assert float(((y[r:r + 1].cpu() - y_ref) ** 2).mean().sqrt()) <= RMS_TOL
+    with pytest.raises(ValueError):
+        m.incremental_forward(initial_input=init, test_inputs=torch.zeros(3, 1, 4), T=8, noise=dev_noise(noise))
+    gq = GoldenCase("mulaw_softmax")
+    mq = cuda_model(gq)
+    Q = gq.cfg.out_channels
+    for layout in ("b1q", "bq1"):
+        oh = torch.zeros(1, 1, Q)
+        oh[:, :, 200] = 1
+        init_q = oh if layout == "b1q" else oh.transpose(1, 2).contiguous()
+        nz = orc.predraw_noise(gq.cfg, 1, 32, 6)
+        yq = mq.incremental_forward(initial_input=init_q, T=32, noise=dev_noise(nz))
+        yq_ref = orc.incremental_forward(gq.cfg, gq.w, initial_input=init_q, T=32,
+                                         noise=orc.replay_from_predrawn(gq.cfg, nz))
+        assert (yq.argmax(1).cpu() == yq_ref.argmax(1)).float().mean().item() >= 0.95

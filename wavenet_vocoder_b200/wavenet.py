@@ -223,8 +223,12 @@ class WaveNet(nn.Module):
             ii = initial_input.to(dev).float()
             if self.scalar_input:
                 initial = ii.reshape(ii.size(0), -1)[:, 0].contiguous()
+                if c is None and test_inputs is None and g is None:
+                    B = initial.size(0)            # nothing else defines the batch (the reference assumes B=1 here)
                 if initial.size(0) == 1 and B > 1:
                     initial = initial.expand(B).contiguous()
+                if initial.size(0) != B:
+                    raise ValueError("initial_input has %d rows but the batch is %d" % (initial.size(0), B))
             else:
                 if ii.size(1) == O:
                     ii = ii.transpose(1, 2)
