@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WN_ABI_VERSION 1
+#define WN_ABI_VERSION 2
 
 typedef enum wn_status {
     WN_OK = 0,
@@ -69,7 +69,8 @@ typedef struct wn_config {
     int32_t num_ctas;             /* 0 = choose; else number of cooperating thread blocks */
     int32_t exchange_copies;      /* 0 = choose; replicas of each exchange vector in L2   */
     int32_t ring_slots;           /* 0 = choose; streaming weight slots in shared memory  */
-    int32_t reserved[8];
+    int32_t cluster_size;         /* 0 = choose; thread blocks per cluster (power of two <= 16) */
+    int32_t reserved[7];
 } wn_config;
 
 /* One residual layer, HOST pointers, fp32, weight-norm already folded (modules.py:13-18).
@@ -104,6 +105,8 @@ typedef struct wn_generate_args {
     const float* g;            /* (B,gin) global conditioning vector (after embedding, wavenet.py:263-268)       */
     const float* initial;      /* scalar input: (B) ; one-hot input: NULL (default index) -- wavenet.py:281-292   */
     int32_t initial_index;     /* one-hot input: start class (reference default 127, wavenet.py:286); <0 = 127     */
+    const int32_t* initial_rows;   /* one-hot input: (B) start class per utterance, overrides initial_index; or NULL */
+    const float* initial_dense;    /* one-hot input: (B,O) dense start vector fed as is (wavenet.py:281-292); or NULL */
     int32_t T_test;            /* teacher-forcing length (wavenet.py:247-258), 0 = free running                    */
     const float* test_scalar;  /* scalar input: (B,T_test)                                   */
     const int32_t* test_index; /* one-hot input given as class ids: (B,T_test)               */
@@ -136,7 +139,9 @@ typedef struct wn_plan_info {
     int64_t streamed_bytes_per_step;   /* bytes the TMA pipeline moves per step (all CTAs)   */
     int64_t launches;                  /* kernels launched by this handle so far             */
     int64_t cond_packed_bytes_per_cta; /* size of the conditioning-weight image of one block */
-    int64_t reserved[6];
+    int64_t bias_packed_bytes_per_cta; /* size of the bias image of one block (cluster engine) */
+    int64_t num_clusters, cluster_size, num_passes, engine;
+    int64_t reserved[1];
 } wn_plan_info;
 
 int32_t wn_abi_version(void);
@@ -155,7 +160,7 @@ int32_t wn_generate(void* handle, const wn_generate_args* args);
 int32_t wn_sync(void* handle);
 
 /* Same call with HOST buffers everywhere a DEVICE pointer is expected above (inputs are copied
- * in, results copied out, synchronous).  This is the end-to-end entry the bench times. */
+ * in, results copied out, synchronous). */
 int32_t wn_generate_host(void* handle, const wn_generate_args* args);
 
 int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out);
@@ -164,11 +169,18 @@ int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out);
  * `cfg` assuming `num_sms` SMs / `smem_per_cta` bytes, and (if `packed` != NULL) writes the
  * packed weight image of thread block `cta` into `packed`: packed_bytes_per_cta bytes (layer
  * blobs + head blob) followed, if the buffer has room, by cond_packed_bytes_per_cta bytes (the
- * local-conditioning rows the conditioning warp reads from L2). */
+ * local-conditioning rows the conditioning warp reads from L2) and bias_packed_bytes_per_cta bytes
+ * (biases of the rows the block finalises). */
 int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
                      wn_plan_info* out);
 int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
                     const wn_weights* w, int32_t cta, float* packed, int64_t packed_floats);
+
+/* Cluster engine only: the raw execution plan (struct Wn6Plan of csrc/wn6_plan.h as int32 words) and its pass
+ * table (struct Wn6Pass, 20 bytes each), for tools and the host tests that replay the packed image.
+ * Returns the number of passes (>= 0) or a negative wn_status. */
+int32_t wn_plan_passes(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
+                       int32_t* plan_words, int32_t max_plan_words, void* passes, int32_t max_passes);
 
 /* Stand-alone samplers over a (B,O,T) head-output tensor (DEVICE), the reference's
  * mixture.py entry points; noise is REPLAY layout with T as given. out: (B,T). */

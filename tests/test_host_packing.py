@@ -111,164 +111,239 @@ def test_planner_rejects_bad_shapes():
 
 
 # ------------------------------------------------------------------------------------------------
-# independent reading of the packed layout (documented in csrc/wn_plan.h / DESIGN.md)
+# independent reading of the packed layout (documented in csrc/wn6_plan.h / DESIGN.md)
 # ------------------------------------------------------------------------------------------------
-def part(rows, P, p):
-    q, r = divmod(rows, P)
+def part(rows, n, p):
+    q, r = divmod(rows, n)
     return p * q + min(p, r), q + (1 if p < r else 0)
 
 
-def cdiv(a, b):
-    return -(-a // b)
+def own(rows, NC, CS, c, r):
+    cb, cc = part(rows, NC, c)
+    ob, oc = part(cc, CS, r)
+    return cb + ob, oc
 
 
-def unquad(grp, nq, K):
-    """[quad][k][4 rows] -> (4*nq, K)"""
-    return grp.reshape(nq, K, 4).transpose(0, 2, 1).reshape(4 * nq, K)
+K_FIRST, K_LAYER, K_TAIL, K_HEAD1, K_HEAD2 = range(5)
 
 
 class PackedModel:
-    """Reads the packed image back with its own arithmetic for the layout documented in
-    csrc/wn_plan.h: first blob [Zx | zb], layer blobs [Zy | Zx | Xo | Td | Sk | zb | xb | sb],
-    tail blob [Td | Sk | sb | Ha | Hab | Hb | Hbb]; every matrix group is [quad][k][4 rows]."""
+    """Replays the cluster engine's dataflow from the packed per-block images with its own arithmetic:
+    K-slices gathered from the values the rank-r blocks of all clusters published, pass tiles
+    [j][lane][4 rows] multiplied with the slice (k = x_off + sub + 16 j), partial sums summed by the row
+    owners in rank order, then bias / conditioning / queued taps / gate / residual exactly as the finaliser
+    warps do."""
 
-    def __init__(self, gc, P):
+    def __init__(self, gc, P, cluster=0):
         cfg = cfg_for(gc, num_ctas=P)
+        cfg.cluster_size = cluster
         self.gc, self.cfg = gc, cfg
+        pl, passes = N.plan_passes(cfg, 1, NSM, SMEM)
+        assert pl.P == P and pl.NC * pl.CS == P
+        self.pl, self.passes = pl, passes
         info = plan_of(cfg)
-        assert info["num_ctas"] == P
-        self.P = P
+        assert info["num_ctas"] == P and info["num_clusters"] == pl.NC and info["cluster_size"] == pl.CS
+        assert info["engine"] == 6 and info["num_passes"] == len(passes)
         c = gc.cfg
         self.L, self.R, self.G2, self.S, self.O = c.layers, c.residual_channels, c.gate_channels // 2, c.skip_out_channels, c.out_channels
         self.kw, self.C = c.kernel_size, max(c.cin_channels, 0)
-        L, R, G2, S, O, kw = self.L, self.R, self.G2, self.S, self.O, self.kw
-        NYm, NXm, NSm, NAm, NBm = cdiv(G2, P), cdiv(R, P), cdiv(S, P), cdiv(S, P), cdiv(O, P)
-        assert (info["rows_y"], info["rows_x"], info["rows_skip"], info["rows_head_a"], info["rows_head_b"]) == \
-            (NYm, NXm, NSm, NAm, NBm)
-        RA = 2 * NYm
-        nqA, nqD = cdiv(RA, 4), cdiv((kw - 1) * RA, 4)
-        nqBO, nqBS, nqHA, nqHB = cdiv(NXm, 4), cdiv(NSm, 4), cdiv(NAm, 4), cdiv(NBm, 4)
-
-        def offsets(sizes):
-            return [int(v) for v in np.concatenate([[0], np.cumsum(sizes)])]
-        fo = offsets([nqA * R * 4, 4 * nqA])
-        lo = offsets([nqA * G2 * 4, nqA * R * 4, nqBO * G2 * 4, nqD * R * 4, nqBS * G2 * 4, 4 * nqA, 4 * nqBO, 4 * nqBS])
-        to = offsets([nqD * R * 4, nqBS * G2 * 4, 4 * nqBS, nqHA * S * 4, 4 * nqHA, nqHB * S * 4, 4 * nqHB])
-        fb, lb, tb = fo[-1], lo[-1], to[-1]
-        assert info["layer_blob_bytes"] == 4 * lb and info["head_blob_bytes"] == 4 * tb
-        nmain = info["packed_bytes_per_cta"] // 4
-        ncond = info["cond_packed_bytes_per_cta"] // 4
-        assert nmain == fb + (L - 1) * lb + tb and ncond == L * nqA * self.C * 4
-        w, keep = weights_struct(gc.sd, L, self.C, max(c.gin_channels, 0))
-        self.blocks = []
+        nmain, ncond, nbias = pl.cta_w_floats, pl.cta_cw_floats, pl.cta_b_floats
+        assert info["packed_bytes_per_cta"] == 4 * nmain and info["cond_packed_bytes_per_cta"] == 4 * ncond
+        assert info["bias_packed_bytes_per_cta"] == 4 * nbias
+        assert nmain == pl.fb_floats + (self.L - 1) * pl.lb_floats + pl.tb_floats
+        w, keep = weights_struct(gc.sd, self.L, self.C, max(c.gin_channels, 0))
+        self.img = []
         for p in range(P):
-            buf = np.zeros(nmain + ncond, dtype=np.float32)
+            buf = np.zeros(nmain + ncond + nbias, dtype=np.float32)
             N.check(N.lib().wn_pack_cta(C.byref(cfg), 1, NSM, SMEM, C.byref(w), p,
                                         buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size))
-            blk = dict(y=part(G2, P, p), x=part(R, P, p), s=part(S, P, p), a=part(S, P, p), b=part(O, P, p), stages=[])
-            b0 = buf[:fb]
-            blk["stages"].append(dict(Zx=unquad(b0[fo[0]:fo[1]], nqA, R), zb=b0[fo[1]:fo[2]]))
-            for s_ in range(1, L):
-                b = buf[fb + (s_ - 1) * lb: fb + s_ * lb]
-                seg = [b[lo[i]:lo[i + 1]] for i in range(8)]
-                blk["stages"].append(dict(Zy=unquad(seg[0], nqA, G2), Zx=unquad(seg[1], nqA, R),
-                                          Xo=unquad(seg[2], nqBO, G2), Td=unquad(seg[3], nqD, R),
-                                          Sk=unquad(seg[4], nqBS, G2), zb=seg[5], xb=seg[6], sb=seg[7]))
-            tbuf = buf[fb + (L - 1) * lb: nmain]
-            seg = [tbuf[to[i]:to[i + 1]] for i in range(7)]
-            blk["tail"] = dict(Td=unquad(seg[0], nqD, R), Sk=unquad(seg[1], nqBS, G2), sb=seg[2],
-                               Ha=unquad(seg[3], nqHA, S), Hab=seg[4], Hb=unquad(seg[5], nqHB, S), Hbb=seg[6])
-            blk["cond"] = [unquad(buf[nmain + l * nqA * self.C * 4: nmain + (l + 1) * nqA * self.C * 4], nqA, self.C)
-                           for l in range(L)] if self.C else None
-            self.blocks.append(blk)
-        self.RA = RA
+            self.img.append(dict(w=buf[:nmain], cw=buf[nmain:nmain + ncond], b=buf[nmain + ncond:]))
         del keep
 
+    def blob(self, p, stage):
+        pl = self.pl
+        i = min(stage, self.L)
+        off = 0 if i == 0 else pl.fb_floats + (i - 1) * pl.lb_floats
+        n = pl.fb_floats if i == 0 else (pl.lb_floats if i < self.L else pl.tb_floats)
+        return self.img[p]["w"][off:off + n]
+
+    def run_stage(self, kind, stage, xin):
+        """xin[r]: the K-slice of rank r (values).  Returns (crit, defer): [P][row][src rank] partial sums."""
+        pl = self.pl
+        crit = np.zeros((pl.P, pl.nrow_c, pl.CS), np.float32)
+        defer = np.zeros((pl.P, pl.nrow_d, pl.CS), np.float32)
+        for p in range(pl.P):
+            c, r = divmod(p, pl.CS)
+            blob = self.blob(p, stage)
+            x = np.zeros(pl.xin_vals + 64, np.float32)
+            x[:len(xin[r])] = xin[r]
+            for wv in range(8):
+                b0 = pl.pass_begin[kind][wv]
+                for ps in self.passes[b0:b0 + pl.pass_count[kind][wv]]:
+                    tile = blob[ps.w_off:ps.w_off + ps.nit * 128].reshape(ps.nit, 32, 4)
+                    for g in range(2):
+                        if ps.owner[g] < 0:
+                            continue
+                        ks = ps.x_off + np.arange(16)[None, :] + 16 * np.arange(ps.nit)[:, None]       # (nit, 16)
+                        sums = np.einsum("jsi,js->i", tile[:, g * 16:(g + 1) * 16, :].astype(np.float64), x[ks].astype(np.float64))
+                        dst = defer if ps.deferred else crit
+                        dst[c * pl.CS + ps.owner[g], ps.dst_row[g]:ps.dst_row[g] + 4, r] = sums.astype(np.float32)
+        return crit, defer
+
     def run_teacher_forced(self, b):
-        """Replay the kernel's staged dataflow for utterance b; returns (O,T) head outputs.
-        Stage s evaluates layer s from (y_{s-1}, x_{s-1}) with conv1x1_out folded into its current
-        tap; the older taps' products and the skip rows of layer s-1 are computed one stage late."""
-        gc, L, R, G2, S, O, kw, P, RA = self.gc, self.L, self.R, self.G2, self.S, self.O, self.kw, self.P, self.RA
+        gc, pl, L, kw = self.gc, self.pl, self.L, self.kw
+        NC, CS, P = pl.NC, pl.CS, pl.P
+        G2, R, S, O = self.G2, self.R, self.S, self.O
+        my, mx, ms, mo, qA, qB, qD, qS = pl.my, pl.mx, pl.ms, pl.mo, pl.qA, pl.qB, pl.qD, pl.qS
         w = gc.w
         T = gc.T
         dil = gc.cfg.dilations()
         first_w = w["first_w"].numpy()
         first_b = w["first_b"].numpy()
-        x_tf = gc.x_tf.numpy()[b]                                  # (C0, T)
+        x_tf = gc.x_tf.numpy()[b]
         c_up = gc.t("c_up")
         g_vec = gc.t("g_vec")
-        gb = None
-        if g_vec is not None:
-            gb = [lay["g_w"].numpy() @ g_vec[b].numpy() for lay in w["layers"]]     # (G,) per layer
-        rings = [[{tap: np.zeros(((kw - 1 - tap) * dil[l], RA), np.float32) for tap in range(kw - 1)}
+        gb = [lay["g_w"].numpy() @ g_vec[b].numpy() for lay in w["layers"]] if g_vec is not None else None
+        rs2 = np.float32(math.sqrt(0.5))
+        rings = [[{tap: np.zeros(((kw - 1 - tap) * dil[l], 2 * my), np.float32) for tap in range(kw - 1)}
                   for l in range(L)] for _ in range(P)]
         out = np.zeros((O, T), np.float32)
-        rs2 = np.float32(math.sqrt(0.5))
 
-        def gate(p, blk, l, z_dyn, t):
-            y0, ny = blk["y"]
-            pre = blk["stages"][l]["zb"][:RA].copy()
-            if gb is not None:
-                for j in range(ny):
-                    pre[2 * j] += gb[l][y0 + j]
-                    pre[2 * j + 1] += gb[l][G2 + y0 + j]
-            if self.C:
-                pre += blk["cond"][l][:RA] @ c_up[b, :, t].numpy()
-            for tap in range(kw - 1):
-                pre += rings[p][l][tap][t % ((kw - 1 - tap) * dil[l])]
-            z = z_dyn + pre
-            return [(y0 + j, np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))) for j in range(ny)]
+        def slices(vec_parts):
+            """vec_parts: list of (published values per block [P][m], m); -> per-rank slices [c][m] concatenated"""
+            res = []
+            for r in range(CS):
+                segs = []
+                for vals, m in vec_parts:
+                    segs.append(np.concatenate([vals[c * CS + r][:m] for c in range(NC)]))
+                res.append(np.concatenate(segs))
+            return res
 
-        def queue_taps(p, Td, layer, xvec, t):
-            for tap in range(kw - 1):
-                D = (kw - 1 - tap) * dil[layer]
-                rings[p][layer][tap][t % D] = Td[tap * RA:(tap + 1) * RA] @ xvec
+        def x0_block(r):
+            v = np.zeros(NC * mx, np.float32)
+            for c in range(NC):
+                base, cnt = own(R, NC, CS, c, r)
+                v[c * mx:c * mx + cnt] = x0[base:base + cnt]
+            return v
 
         for t in range(T):
-            x_prev = first_w @ x_tf[:, t] + first_b                # x_0, known to every block
-            y_prev = np.zeros(G2, np.float32)
-            for p, blk in enumerate(self.blocks):                  # stage 0
-                for k, v in gate(p, blk, 0, blk["stages"][0]["Zx"][:RA] @ x_prev, t):
-                    y_prev[k] = v
-            skipacc = [None] * P
-            for s_ in range(1, L):
-                y_new = np.zeros(G2, np.float32)
-                x_new = np.zeros(R, np.float32)
-                for p, blk in enumerate(self.blocks):
-                    st = blk["stages"][s_]
-                    for k, v in gate(p, blk, s_, st["Zy"][:RA] @ y_prev + st["Zx"][:RA] @ x_prev, t):
-                        y_new[k] = v
-                    x0, nx = blk["x"]
-                    x_new[x0:x0 + nx] = (st["Xo"][:nx] @ y_prev + st["xb"][:nx] + x_prev[x0:x0 + nx]) * rs2
-                    queue_taps(p, st["Td"], s_ - 1, x_prev, t)     # deferred
-                    s0, ns = blk["s"]
-                    h = st["Sk"][:ns] @ y_prev + st["sb"][:ns]
-                    skipacc[p] = h if s_ == 1 else skipacc[p] + h
-                y_prev, x_prev = y_new, x_new
-            sk = np.zeros(S, np.float32)
-            for p, blk in enumerate(self.blocks):                  # stage L
-                tl = blk["tail"]
-                s0, ns = blk["s"]
-                h = tl["Sk"][:ns] @ y_prev + tl["sb"][:ns]
+            x0 = first_w @ x_tf[:, t] + first_b
+            ypub = np.zeros((P, my), np.float32)
+            xpub = np.zeros((P, mx), np.float32)
+            for p in range(P):
+                c, r = divmod(p, CS)
+                base, cnt = own(R, NC, CS, c, r)
+                xpub[p, :cnt] = x0[base:base + cnt]
+            skipacc = np.zeros((P, ms), np.float32)
+            for s_ in range(0, L):
+                kind = K_FIRST if s_ == 0 else K_LAYER
+                if s_ == 0:
+                    xin = [np.concatenate([np.zeros(NC * my, np.float32), x0_block(r)]) for r in range(CS)]
+                else:
+                    xin = slices([(ypub, my), (xpub, mx)])
+                    for r in range(CS):
+                        assert len(xin[r]) == pl.Ky + pl.Kx
+                crit, defer = self.run_stage(kind, s_, xin)
+                ynew = np.zeros((P, my), np.float32)
+                xnew = np.zeros((P, mx), np.float32)
+                for p in range(P):
+                    c, r = divmod(p, CS)
+                    bias = self.img[p]["b"]
+                    y0, ny = own(G2, NC, CS, c, r)
+                    pre = bias[pl.bo_zb + s_ * 4 * qA: pl.bo_zb + s_ * 4 * qA + 2 * my].copy()
+                    for j in range(ny):
+                        if gb is not None:
+                            pre[2 * j] += gb[s_][y0 + j]
+                            pre[2 * j + 1] += gb[s_][G2 + y0 + j]
+                    if self.C:
+                        cw = self.img[p]["cw"][s_ * qA * self.C * 4:(s_ + 1) * qA * self.C * 4].reshape(qA, self.C, 4)
+                        cw = cw.transpose(0, 2, 1).reshape(4 * qA, self.C)[:2 * my]
+                        pre += cw @ c_up[b, :, t].numpy()
+                    for tap in range(kw - 1):
+                        pre += rings[p][s_][tap][t % ((kw - 1 - tap) * dil[s_])]
+                    z = crit[p, :2 * my].sum(axis=1) + pre
+                    for j in range(ny):
+                        ynew[p, j] = np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))
+                    if s_ >= 1:
+                        x0r, nx = own(R, NC, CS, c, r)
+                        o = crit[p, 4 * qA:4 * qA + mx].sum(axis=1) + bias[pl.bo_xb + s_ * 4 * qB: pl.bo_xb + s_ * 4 * qB + mx]
+                        xnew[p, :nx] = ((o + xpub[p]) * rs2)[:nx]
+                        layer = s_ - 1
+                        for tap in range(kw - 1):
+                            D = (kw - 1 - tap) * dil[layer]
+                            rings[p][layer][tap][t % D] = defer[p, tap * 2 * my:(tap + 1) * 2 * my].sum(axis=1)
+                        h = defer[p, 4 * qD:4 * qD + ms].sum(axis=1) + bias[pl.bo_sb + layer * 4 * qS: pl.bo_sb + layer * 4 * qS + ms]
+                        skipacc[p] = h if layer == 0 else skipacc[p] + h
+                ypub = ynew
+                if s_ >= 1:
+                    xpub = xnew
+            # stage L: skip of the last layer
+            xin = slices([(ypub, my), (xpub, mx)])
+            crit, defer = self.run_stage(K_TAIL, L, xin)
+            skpub = np.zeros((P, ms), np.float32)
+            for p in range(P):
+                c, r = divmod(p, CS)
+                bias = self.img[p]["b"]
+                h = crit[p, :ms].sum(axis=1) + bias[pl.bo_sb + (L - 1) * 4 * qS: pl.bo_sb + (L - 1) * 4 * qS + ms]
                 tot = h if L == 1 else skipacc[p] + h
-                sk[s0:s0 + ns] = np.maximum(tot * np.float32(math.sqrt(1.0 / L)), 0)
-                queue_taps(p, tl["Td"], L - 1, x_prev, t)
-            h1 = np.zeros(S, np.float32)
-            for blk in self.blocks:
-                a0, na = blk["a"]
-                h1[a0:a0 + na] = np.maximum(blk["tail"]["Ha"][:na] @ sk + blk["tail"]["Hab"][:na], 0)
-            for blk in self.blocks:
-                b0, nb = blk["b"]
-                out[b0:b0 + nb, t] = blk["tail"]["Hb"][:nb] @ h1 + blk["tail"]["Hbb"][:nb]
+                s0, ns = own(S, NC, CS, c, r)
+                skpub[p, :ns] = np.maximum(tot * np.float32(math.sqrt(1.0 / L)), 0)[:ns]
+                for tap in range(kw - 1):
+                    D = (kw - 1 - tap) * dil[L - 1]
+                    rings[p][L - 1][tap][t % D] = defer[p, tap * 2 * my:(tap + 1) * 2 * my].sum(axis=1)
+            crit, _ = self.run_stage(K_HEAD1, L + 1, slices([(skpub, ms)]))
+            h1pub = np.zeros((P, ms), np.float32)
+            for p in range(P):
+                c, r = divmod(p, CS)
+                a0, na = own(S, NC, CS, c, r)
+                h1pub[p, :na] = np.maximum(crit[p, :ms].sum(axis=1) + self.img[p]["b"][pl.bo_ha:pl.bo_ha + ms], 0)[:na]
+            crit, _ = self.run_stage(K_HEAD2, L + 2, slices([(h1pub, ms)]))
+            for p in range(P):
+                c, r = divmod(p, CS)
+                b0, nb = own(O, NC, CS, c, r)
+                out[b0:b0 + nb, t] = (crit[p, :mo].sum(axis=1) + self.img[p]["b"][pl.bo_hb:pl.bo_hb + mo])[:nb]
         return out
 
 
-@pytest.mark.parametrize("name,P", [("mol_cond", 5), ("mol_cond", 32), ("mulaw_softmax", 16),
-                                    ("gauss_speaker", 3), ("mixgauss", 7), ("mol_upsample", 24)])
-def test_packed_image_replays_reference(name, P):
+@pytest.mark.parametrize("name,P,cluster", [("mol_cond", 5, 0), ("mol_cond", 32, 8), ("mol_cond", 16, 4),
+                                            ("mulaw_softmax", 16, 0), ("gauss_speaker", 3, 0), ("mixgauss", 6, 2),
+                                            ("mol_upsample", 24, 0), ("mol_cond", 16, 16)])
+def test_packed_image_replays_reference(name, P, cluster):
     gc = GoldenCase(name)
-    pm = PackedModel(gc, P)
+    pm = PackedModel(gc, P, cluster)
+    if cluster:
+        assert pm.pl.CS == cluster
     got = pm.run_teacher_forced(0)
     ref = gc.arr["params_tf"][0]
     assert got.shape == ref.shape
     assert float(np.abs(got - ref).max()) <= 2e-5
+
+
+def test_pass_lists_cover_every_row_once():
+    """Every (owner, row slot) of every job receives exactly one tile per stage kind, critical passes precede
+    deferred ones in every warp, and tiles do not overlap inside a blob."""
+    cfg = make_config(layers=24, stacks=4, residual_channels=512, gate_channels=512, skip_out_channels=256,
+                      out_channels=30, kernel_size=3, cin_channels=80, gin_channels=-1, scalar_input=True,
+                      output_distribution="Logistic")
+    for batch in (1, 8):
+        pl, passes = N.plan_passes(cfg, batch)
+        assert (pl.NC, pl.CS, pl.P, pl.BT) == (16, 8, 128, batch)
+        for kind in range(5):
+            seen = {}
+            spans = []
+            for wv in range(8):
+                b0, n, nc = pl.pass_begin[kind][wv], pl.pass_count[kind][wv], pl.pass_crit[kind][wv]
+                for i, ps in enumerate(passes[b0:b0 + n]):
+                    assert (ps.deferred == 0) == (i < nc)
+                    spans.append((ps.w_off, ps.w_off + ps.nit * 128))
+                    for g in range(2):
+                        if ps.owner[g] >= 0:
+                            key = (ps.deferred, ps.owner[g], ps.dst_row[g])
+                            assert key not in seen
+                            seen[key] = ps.job
+            rows_c = {(o, r) for (d, o, r) in seen if d == 0}
+            rows_d = {(o, r) for (d, o, r) in seen if d == 1}
+            assert len(rows_c) * 4 == pl.rows_c[kind] * pl.CS and len(rows_d) * 4 == pl.rows_d[kind] * pl.CS
+            if kind in (K_FIRST, K_LAYER):
+                spans.sort()
+                assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))

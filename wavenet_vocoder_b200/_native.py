@@ -15,10 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libwn.so")
 SOURCES = [os.path.join(HERE, "csrc", "wn_host.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "wn_plan.h"), os.path.join(HERE, "csrc", "wn_kernel.cuh"),
-           os.path.join(ROOT, "include", "wn.h")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("wn_plan.h", "wn_kernel.cuh", "wn6_plan.h", "wn6_kernel.cuh",
+                                                     "wn6_host.cuh")] + [os.path.join(ROOT, "include", "wn.h")]
 
-WN_ABI_VERSION = 1
+WN_ABI_VERSION = 2
 WN_INPUT_SCALAR, WN_INPUT_ONEHOT = 0, 1
 WN_HEAD_MOL, WN_HEAD_GAUSS, WN_HEAD_SOFTMAX = 0, 1, 2
 WN_NOISE_REPLAY, WN_NOISE_PHILOX = 0, 1
@@ -32,7 +32,7 @@ class wn_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "layers", "stacks", "residual_channels", "gate_channels", "skip_channels",
         "out_channels", "kernel_size", "cin_channels", "gin_channels", "input_kind", "head_kind",
-        "device", "num_ctas", "exchange_copies", "ring_slots")] + [("reserved", C.c_int32 * 8)]
+        "device", "num_ctas", "exchange_copies", "ring_slots", "cluster_size")] + [("reserved", C.c_int32 * 7)]
 
 
 class wn_layer_weights(C.Structure):
@@ -49,7 +49,8 @@ class wn_generate_args(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("T", C.c_int32),
         ("c", C.c_void_p), ("g", C.c_void_p), ("initial", C.c_void_p),
-        ("initial_index", C.c_int32), ("T_test", C.c_int32),
+        ("initial_index", C.c_int32), ("initial_rows", C.c_void_p), ("initial_dense", C.c_void_p),
+        ("T_test", C.c_int32),
         ("test_scalar", C.c_void_p), ("test_index", C.c_void_p), ("test_dense", C.c_void_p),
         ("flags", C.c_uint32), ("noise_kind", C.c_int32), ("seed", C.c_uint64),
         ("noise_u1", C.c_void_p), ("noise_u2", C.c_void_p), ("noise_z", C.c_void_p),
@@ -67,16 +68,61 @@ class wn_plan_info(C.Structure):
         "exchanges_per_step", "rings_in_smem")] + [(n, C.c_int64) for n in (
             "smem_bytes", "layer_blob_bytes", "head_blob_bytes", "packed_bytes_per_cta",
             "weight_bytes_per_step", "flops_per_sample", "streamed_bytes_per_step", "launches",
-            "cond_packed_bytes_per_cta")] + [("reserved", C.c_int64 * 6)]
+            "cond_packed_bytes_per_cta", "bias_packed_bytes_per_cta", "num_clusters", "cluster_size",
+            "num_passes", "engine")] + [("reserved", C.c_int64 * 1)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class Wn6Pass(C.Structure):
+    """Mirror of struct Wn6Pass (csrc/wn6_plan.h): one warp pass = two row quads x nit k-steps."""
+    _fields_ = [("w_off", C.c_int32), ("nit", C.c_int16), ("x_off", C.c_int16), ("dst_row", C.c_int16 * 2),
+                ("owner", C.c_int8 * 2), ("deferred", C.c_int8), ("job", C.c_int8), ("quad", C.c_int16 * 2)]
+
+
+_NKIND, _NCW = 5, 8
+
+
+class Wn6Plan(C.Structure):
+    """Mirror of struct Wn6Plan (csrc/wn6_plan.h); filled by wn_plan_passes."""
+    _fields_ = ([(n, C.c_int32) for n in ("L", "per_stack", "R", "G", "G2", "S", "O", "kw", "C", "gin", "input_kind",
+                                          "head_kind", "Kmix")] + [("skip_scale", C.c_float)] +
+                [(n, C.c_int32) for n in ("NC", "CS", "P", "BT", "my", "mx", "ms", "mo", "qA", "qB", "qD", "qS", "qHA",
+                                          "qHB", "Ky", "Kx", "Ksk", "Kh2", "xin_vals", "NS", "rs_yx", "rs_sk", "rs_h2")] +
+                [(n, C.c_int64) for n in ("ex_yx", "ex_sk", "ex_h1", "ex_h2", "ex_pairs")] +
+                [("nrow_c", C.c_int32), ("nrow_d", C.c_int32), ("rows_c", C.c_int32 * _NKIND),
+                 ("rows_d", C.c_int32 * _NKIND), ("npass", C.c_int32),
+                 ("pass_begin", (C.c_int32 * _NCW) * _NKIND), ("pass_count", (C.c_int32 * _NCW) * _NKIND),
+                 ("pass_crit", (C.c_int32 * _NCW) * _NKIND)] +
+                [(n, C.c_int32) for n in ("fb_floats", "lb_floats", "tb_floats", "slot_floats")] +
+                [("cta_w_floats", C.c_int64)] +
+                [(n, C.c_int32) for n in ("nblobs", "nres", "nring", "bo_zb", "bo_xb", "bo_sb", "bo_ha", "bo_hb",
+                                          "cta_b_floats")] +
+                [("cta_cw_floats", C.c_int64), ("ring_in_smem", C.c_int32), ("ring_pos_total", C.c_int64)] +
+                [(n, C.c_int32) for n in ("sm_bar", "sm_misc", "sm_pass", "sm_ringtab", "sm_xin", "sm_part", "sm_dpart",
+                                          "sm_sb", "sm_pre", "sm_cond", "sm_bias", "sm_skipacc", "sm_xown", "sm_hs",
+                                          "sm_noise", "sm_in", "sm_x0w", "sm_ring", "sm_slots", "smem_bytes")])
+
+
+def plan_passes(cfg, batch=1, num_sms=148, smem=232448):
+    """(Wn6Plan, [Wn6Pass]) the planner of the cluster engine produces for `cfg` (no GPU needed)."""
+    pl = Wn6Plan()
+    n = lib().wn_plan_passes(C.byref(cfg), batch, num_sms, smem, C.cast(C.byref(pl), _i32p), C.sizeof(pl) // 4, None, 0)
+    if n < 0:
+        check(n)
+    ps = (Wn6Pass * max(n, 1))()
+    n = lib().wn_plan_passes(C.byref(cfg), batch, num_sms, smem, C.cast(C.byref(pl), _i32p), C.sizeof(pl) // 4,
+                             C.cast(ps, C.c_void_p), n)
+    if n < 0:
+        check(n)
+    return pl, list(ps)[:n]
+
+
 # every symbol include/wn.h declares (tests check the .so exports all of them)
 EXPORTS = ["wn_abi_version", "wn_last_error", "wn_create", "wn_destroy", "wn_load_weights",
            "wn_generate", "wn_sync", "wn_generate_host", "wn_get_plan", "wn_plan_only",
-           "wn_pack_cta", "wn_sample_mol", "wn_sample_gauss"]
+           "wn_pack_cta", "wn_plan_passes", "wn_sample_mol", "wn_sample_gauss"]
 
 
 def nvcc_command(out=LIB_PATH):
@@ -133,6 +179,8 @@ def lib():
     L.wn_plan_only.argtypes = [C.POINTER(wn_config), C.c_int32, C.c_int32, C.c_int64, C.POINTER(wn_plan_info)]
     L.wn_pack_cta.argtypes = [C.POINTER(wn_config), C.c_int32, C.c_int32, C.c_int64, C.POINTER(wn_weights),
                               C.c_int32, _f32p, C.c_int64]
+    L.wn_plan_passes.argtypes = [C.POINTER(wn_config), C.c_int32, C.c_int32, C.c_int64, _i32p, C.c_int32,
+                                 C.c_void_p, C.c_int32]
     L.wn_sample_mol.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]
     L.wn_sample_gauss.argtypes = L.wn_sample_mol.argtypes

@@ -14,6 +14,8 @@
 #include "../../include/wn.h"
 #include "wn_plan.h"
 #include "wn_kernel.cuh"
+#include "wn6_plan.h"
+#include "wn6_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -30,6 +32,16 @@ static int32_t fail(int32_t code, const std::string& msg) {
             return fail(WN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
         }                                                                                       \
     } while (0)
+
+// restores the caller's current CUDA device on scope exit (the library must not change it as a side effect)
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -281,8 +293,7 @@ struct Folded {
     std::vector<std::vector<float>> V, M, zb;     // per layer (V[0] is the plain current tap)
 };
 
-static void fold_layers(const WnPlan& pl, const wn_weights& w, Folded& f) {
-    const int L = pl.L, G = pl.G, R = pl.R, G2 = pl.G2, kw = pl.kw;
+static void fold_layers(int L, int G, int R, int G2, int kw, const wn_weights& w, Folded& f) {
     const float rs2 = 0.70710678118654752440f;
     f.V.assign(L, {});
     f.M.assign(L, {});
@@ -410,11 +421,24 @@ static int32_t check_weights(const wn_config& c, const wn_weights* w) {
     return WN_OK;
 }
 
+#include "wn6_host.cuh"
+
+// which kernel generation: 6 = thread-block clusters + DSMEM (default), 5 = the round-1 all-poll kernel
+static int engine_choice() { return env_int("WN_ENGINE", 6) == 5 ? 5 : 6; }
+
 // ------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------
 struct WnHandle {
     wn_config cfg;
+    int engine = 6;
+    Wn6Plan base6;                // plan for BT=1 (grid, passes and blob layout are batch independent)
+    std::vector<Wn6Pass> passes6;
+    float* d_bpack = nullptr;
+    Wn6Pass* d_passes = nullptr;
+    int max_clusters = 0;
+    bool attr6_set[4] = {};
+    bool coop_with_clusters = true;
     int num_sms = 0;
     long long smem_cap = 0;
     bool have_weights = false;
@@ -447,6 +471,7 @@ static int32_t ensure(T** ptr, size_t* have, size_t need) {
     return WN_OK;
 }
 
+static int max_tile(int engine) { return std::max(1, std::min(8, env_int("WN_MAX_TILE", engine == 6 ? 8 : 4))); }
 static int bt_index(int BT) { return BT == 1 ? 0 : BT == 2 ? 1 : BT == 4 ? 2 : 3; }
 
 static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
@@ -578,6 +603,172 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     return WN_OK;
 }
 
+static void fill_info6(const wn_config& c, const Wn6Plan& pl, wn_plan_info* out) {
+    memset(out, 0, sizeof(*out));
+    out->num_ctas = pl.P;
+    out->threads_per_cta = WN6_NTHREADS;
+    out->batch_tile = pl.BT;
+    out->rows_y = pl.my;
+    out->rows_x = pl.mx;
+    out->rows_skip = pl.ms;
+    out->rows_head_a = pl.ms;
+    out->rows_head_b = pl.mo;
+    out->resident_blobs = pl.nres;
+    out->ring_slots = pl.nring;
+    out->blobs_per_step = pl.nblobs;
+    out->exchange_copies = 1;
+    out->exchanges_per_step = pl.NS;
+    out->rings_in_smem = pl.ring_in_smem;
+    out->smem_bytes = pl.smem_bytes;
+    out->layer_blob_bytes = (int64_t)pl.lb_floats * 4;
+    out->head_blob_bytes = (int64_t)pl.tb_floats * 4;
+    out->packed_bytes_per_cta = (int64_t)pl.cta_w_floats * 4;
+    out->cond_packed_bytes_per_cta = (int64_t)pl.cta_cw_floats * 4;
+    out->bias_packed_bytes_per_cta = (int64_t)pl.cta_b_floats * 4;
+    out->num_clusters = pl.NC;
+    out->cluster_size = pl.CS;
+    out->num_passes = pl.npass;
+    out->engine = 6;
+    const int64_t cin0 = (c.input_kind == WN_INPUT_SCALAR) ? 1 : pl.O;
+    // MAC = C0*R + L*(G*kw*R + G*C + S*G/2 + R*G/2) + S*S + O*S ; weights = MAC + biases
+    const int64_t mac = cin0 * pl.R + (int64_t)pl.L * ((int64_t)pl.G * pl.kw * pl.R + (int64_t)pl.G * pl.C +
+                                                        (int64_t)pl.S * pl.G2 + (int64_t)pl.R * pl.G2) +
+                        (int64_t)pl.S * pl.S + (int64_t)pl.O * pl.S;
+    const int64_t biases = pl.R + (int64_t)pl.L * (pl.G + pl.S + pl.R) + pl.S + pl.O;
+    out->flops_per_sample = 2 * mac;
+    out->weight_bytes_per_step = 4 * (mac + biases);
+    int64_t streamed = 0;
+    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += wn6_blob_floats(pl, i) * 4LL;
+    out->streamed_bytes_per_step = streamed * pl.P;
+}
+
+static const void* kernel6_for(int BT) {
+    switch (BT) {
+        case 1: return (const void*)wn6::wn6_kernel<1>;
+        case 2: return (const void*)wn6::wn6_kernel<2>;
+        case 4: return (const void*)wn6::wn6_kernel<4>;
+        default: return (const void*)wn6::wn6_kernel<8>;
+    }
+}
+
+static int32_t prepare_kernel6(WnHandle* h, int BT, int CS) {
+    const int ai = bt_index(BT);
+    if (h->attr6_set[ai]) return WN_OK;
+    const void* fn = kernel6_for(BT);
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
+    if (CS > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    h->attr6_set[ai] = true;
+    return WN_OK;
+}
+
+static int32_t launch_chunk6(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
+    Wn6Plan pl;
+    std::vector<Wn6Pass> passes;
+    std::vector<int> rt;
+    int32_t rc = build_plan6(h->cfg, Bc, h->num_sms, h->smem_cap, h->max_clusters, pl, passes, rt);
+    if (rc) return rc;
+    if (pl.P != h->base6.P || pl.CS != h->base6.CS || pl.lb_floats != h->base6.lb_floats || pl.npass != h->base6.npass)
+        return fail(WN_ERR_STATE, "plan changed between weight upload and generate");
+    const int BT = pl.BT;
+    const wn_config& c = h->cfg;
+    const size_t xb = (size_t)pl.ex_pairs * sizeof(uint2);
+    rc = ensure(&h->d_xbuf, &h->xbuf_bytes, xb);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_xbuf, 0, xb, st));     // zeroed every call so stale tags can never match
+    if (!pl.ring_in_smem) {
+        const size_t rb = std::max<size_t>(16, (size_t)pl.P * pl.ring_pos_total * 4 * pl.qA * BT * sizeof(float));
+        rc = ensure(&h->d_ring, &h->ring_bytes, rb);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->d_ring, 0, rb, st));
+    }
+    Wn6Ptrs pp;
+    memset(&pp, 0, sizeof(pp));
+    if (c.gin_channels > 0) {
+        if (!a->g) return fail(WN_ERR_INVALID, "g is required (gin_channels > 0), cf. train.py:72-80 sanity_check");
+        const size_t gb = (size_t)Bc * pl.L * pl.G * sizeof(float);
+        rc = ensure(&h->d_gbias, &h->gbias_bytes, gb);
+        if (rc) return rc;
+        wn6::wn6_gbias_kernel<<<dim3(pl.L, Bc), 128, 0, st>>>(h->d_wg, a->g + (size_t)b0 * c.gin_channels, h->d_gbias,
+                                                            pl.L, pl.G, c.gin_channels);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        pp.gbias = h->d_gbias;
+    }
+    const int T = a->T, Tt = a->T_test, O = pl.O, K = pl.Kmix;
+    pp.wpack = h->d_wpack;
+    pp.cwpack = h->d_cwpack;
+    pp.bpack = h->d_bpack;
+    pp.passes = h->d_passes;
+    pp.first_w = h->d_first_w;
+    pp.first_b = h->d_first_b;
+    pp.xbuf = h->d_xbuf;
+    pp.ring_g = h->d_ring;
+    pp.ringtab = h->d_ringtab;
+    pp.err = h->d_err;
+    pp.c = a->c ? a->c + (size_t)b0 * T * pl.C : nullptr;
+    pp.initial = a->initial ? a->initial + b0 : nullptr;
+    pp.initial_dense = a->initial_dense ? a->initial_dense + (size_t)b0 * O : nullptr;
+    pp.initial_rows = a->initial_rows ? a->initial_rows + b0 : nullptr;
+    pp.test_scalar = a->test_scalar ? a->test_scalar + (size_t)b0 * Tt : nullptr;
+    pp.test_index = a->test_index ? a->test_index + (size_t)b0 * Tt : nullptr;
+    pp.test_dense = a->test_dense ? a->test_dense + (size_t)b0 * Tt * O : nullptr;
+    // noise is (T, Btotal, .): the kernel indexes with the total batch, so shift by the row
+    pp.u1 = a->noise_u1 ? a->noise_u1 + (size_t)b0 * K : nullptr;
+    pp.u2 = a->noise_u2 ? a->noise_u2 + b0 : nullptr;
+    pp.z = a->noise_z ? a->noise_z + b0 : nullptr;
+    pp.e = a->noise_e ? a->noise_e + (size_t)b0 * O : nullptr;
+    pp.out_scalar = a->out_scalar ? a->out_scalar + (size_t)b0 * T : nullptr;
+    pp.out_index = a->out_index ? a->out_index + (size_t)b0 * T : nullptr;
+    pp.out_dense = a->out_dense ? a->out_dense + (size_t)b0 * O * T : nullptr;
+    pp.params_out = a->params_out ? a->params_out + (size_t)b0 * O * T : nullptr;
+    pp.B = Bc;
+    pp.Btot = a->B;
+    pp.b0 = b0;
+    pp.T = T;
+    pp.T_test = Tt;
+    pp.initial_index = a->initial_index < 0 ? 127 : a->initial_index;   // wavenet.py:286
+    pp.flags = a->flags;
+    pp.noise_kind = a->noise_kind;
+    pp.seed = a->seed;
+    pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
+    pp.prof = nullptr;
+    if (env_int("WN_PROF", 0)) {
+        const size_t pb = (size_t)pl.P * 16 * sizeof(long long);
+        rc = ensure(&h->d_prof, &h->prof_bytes, pb);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, pb, st));
+        pp.prof = h->d_prof;
+    }
+    rc = prepare_kernel6(h, BT, pl.CS);
+    if (rc) return rc;
+    void* kargs[2] = {(void*)&pl, (void*)&pp};
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(pl.P);
+    lc.blockDim = dim3(WN6_NTHREADS);
+    lc.dynamicSmemBytes = (size_t)pl.smem_bytes;
+    lc.stream = st;
+    cudaLaunchAttribute la[2];
+    int na = 0;
+    la[na].id = cudaLaunchAttributeClusterDimension;
+    la[na].val.clusterDim.x = (unsigned)pl.CS;
+    la[na].val.clusterDim.y = 1;
+    la[na].val.clusterDim.z = 1;
+    ++na;
+    // cooperative launch: the runtime refuses to start unless all blocks are co-resident, which the
+    // spin-wait exchanges require
+    if (h->coop_with_clusters) {
+        la[na].id = cudaLaunchAttributeCooperative;
+        la[na].val.cooperative = 1;
+        ++na;
+    }
+    lc.attrs = la;
+    lc.numAttrs = na;
+    CUDA_TRY(cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs));
+    h->launches++;
+    return WN_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -588,6 +779,15 @@ const char* wn_last_error(void) { return g_err.c_str(); }
 
 int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, wn_plan_info* out) {
     if (!cfg || !out) return fail(WN_ERR_INVALID, "null argument");
+    if (engine_choice() == 6) {
+        Wn6Plan pl6;
+        std::vector<Wn6Pass> ps;
+        std::vector<int> rt6;
+        int32_t rc6 = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl6, ps, rt6);
+        if (rc6) return rc6;
+        fill_info6(*cfg, pl6, out);
+        return WN_OK;
+    }
     WnPlan pl;
     std::vector<int> rt;
     int32_t rc = build_plan(*cfg, batch, num_sms, smem_per_cta, pl, rt);
@@ -596,9 +796,49 @@ int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64
     return WN_OK;
 }
 
+int32_t wn_plan_passes(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, int32_t* plan_words,
+                       int32_t max_plan_words, void* passes, int32_t max_passes) {
+    if (!cfg) return fail(WN_ERR_INVALID, "null argument");
+    Wn6Plan pl;
+    std::vector<Wn6Pass> ps;
+    std::vector<int> rt;
+    int32_t rc = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl, ps, rt);
+    if (rc) return rc;
+    if (plan_words) {
+        const int n = std::min<int>(max_plan_words, (int)(sizeof(Wn6Plan) / 4));
+        memcpy(plan_words, &pl, (size_t)n * 4);
+    }
+    if (passes) {
+        if (max_passes < pl.npass) return fail(WN_ERR_INVALID, "pass buffer too small");
+        memcpy(passes, ps.data(), ps.size() * sizeof(Wn6Pass));
+    }
+    return pl.npass;
+}
+
 int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, const wn_weights* w,
                     int32_t cta, float* packed, int64_t packed_floats) {
     if (!cfg || !packed) return fail(WN_ERR_INVALID, "null argument");
+    if (engine_choice() == 6) {
+        Wn6Plan pl6;
+        std::vector<Wn6Pass> ps;
+        std::vector<int> rt6;
+        int32_t rc6 = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl6, ps, rt6);
+        if (rc6) return rc6;
+        rc6 = check_weights(*cfg, w);
+        if (rc6) return rc6;
+        if (cta < 0 || cta >= pl6.P) return fail(WN_ERR_INVALID, "cta out of range");
+        if (packed_floats < pl6.cta_w_floats) return fail(WN_ERR_INVALID, "packed buffer too small");
+        Folded fo;
+        fold_layers(pl6.L, pl6.G, pl6.R, pl6.G2, pl6.kw, *w, fo);
+        pack6_cta(pl6, ps, *w, fo, cta, packed);
+        long long off = pl6.cta_w_floats;
+        if (packed_floats >= off + pl6.cta_cw_floats) {
+            pack6_cw(pl6, *w, cta, packed + off);
+            off += pl6.cta_cw_floats;
+            if (packed_floats >= off + pl6.cta_b_floats) pack6_bias(pl6, *w, fo, cta, packed + off);
+        }
+        return WN_OK;
+    }
     WnPlan pl;
     std::vector<int> rt;
     int32_t rc = build_plan(*cfg, batch, num_sms, smem_per_cta, pl, rt);
@@ -608,7 +848,7 @@ int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_
     if (cta < 0 || cta >= pl.P) return fail(WN_ERR_INVALID, "cta out of range");
     if (packed_floats < pl.cta_w_floats) return fail(WN_ERR_INVALID, "packed buffer too small");
     Folded fo;
-    fold_layers(pl, *w, fo);
+    fold_layers(pl.L, pl.G, pl.R, pl.G2, pl.kw, *w, fo);
     pack_cta(pl, *w, fo, cta, packed);
     if (packed_floats >= pl.cta_w_floats + pl.cta_cw_floats) pack_cw_cta(pl, *w, cta, packed + pl.cta_w_floats);
     return WN_OK;
@@ -623,7 +863,7 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
         return fail(WN_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
                                      " (libwn has no CPU path; it needs an sm_100 GPU)");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(WN_ERR_INVALID, "device ordinal out of range");
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10)
@@ -634,17 +874,49 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
     if (!coop) return fail(WN_ERR_CUDA, "device does not support cooperative launch");
     WnHandle* h = new WnHandle();
     h->cfg = *cfg;
+    h->engine = engine_choice();
     h->num_sms = prop.multiProcessorCount;
     h->smem_cap = (long long)prop.sharedMemPerBlockOptin;
-    int32_t rc = build_plan(h->cfg, 1, h->num_sms, h->smem_cap, h->base, h->ringtab);
+    int32_t rc;
+    if (h->engine == 6) {
+        // first plan with the default cluster budget, then ask the runtime how many clusters really fit
+        rc = build_plan6(h->cfg, 1, h->num_sms, h->smem_cap, 0, h->base6, h->passes6, h->ringtab);
+        if (rc == WN_OK && h->cfg.num_ctas <= 0 && env_int("WN_NUM_CTAS", 0) <= 0) {
+            const int CS = h->base6.CS;
+            if (prepare_kernel6(h, 1, CS) == WN_OK) {
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof(lc));
+                lc.gridDim = dim3(h->base6.P);
+                lc.blockDim = dim3(WN6_NTHREADS);
+                lc.dynamicSmemBytes = (size_t)h->smem_cap;
+                cudaLaunchAttribute la[1];
+                la[0].id = cudaLaunchAttributeClusterDimension;
+                la[0].val.clusterDim.x = (unsigned)CS;
+                la[0].val.clusterDim.y = 1;
+                la[0].val.clusterDim.z = 1;
+                lc.attrs = la;
+                lc.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, kernel6_for(1), &lc) == cudaSuccess && ncl > 0) {
+                    h->max_clusters = ncl;
+                    if (ncl < h->base6.NC)
+                        rc = build_plan6(h->cfg, 1, h->num_sms, h->smem_cap, ncl, h->base6, h->passes6, h->ringtab);
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
+        h->coop_with_clusters = env_int("WN_COOP", 1) != 0;
+    } else {
+        rc = build_plan(h->cfg, 1, h->num_sms, h->smem_cap, h->base, h->ringtab);
+    }
     if (rc) {
         delete h;
         return rc;
     }
-    if (env_int("WN_L2_PERSIST", 0) && prop.persistingL2CacheMaxSize > 0) {
+    if (h->engine == 5 && env_int("WN_L2_PERSIST", 0) && prop.persistingL2CacheMaxSize > 0) {
         // Optional (WN_L2_PERSIST=1): pin as much of the packed weight image as allowed in the persisting part of
-        // the 126 MB L2.  The cyclic 112 MB/sample stream otherwise evicts itself (ncu: 16 % hit rate), but the
-        // weights are not on the critical path: measured 44.7 us/sample with the window vs 44.1 without, so off.
+        // the 126 MB L2.  Measured 44.7 us/sample with the window vs 44.1 without, so off.
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
             h->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
             h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
@@ -652,8 +924,14 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
             cudaGetLastError();
         }
     }
-    h->cfg.num_ctas = h->base.P;          // freeze the partition so every batch tile agrees with the packing
-    h->cfg.exchange_copies = h->base.ncopy;
+    // freeze the partition so every batch tile agrees with the packing
+    if (h->engine == 6) {
+        h->cfg.num_ctas = h->base6.P;
+        h->cfg.cluster_size = h->base6.CS;
+    } else {
+        h->cfg.num_ctas = h->base.P;
+        h->cfg.exchange_copies = h->base.ncopy;
+    }
     if (cudaMalloc((void**)&h->d_err, 16) != cudaSuccess || cudaMemset(h->d_err, 0, 16) != cudaSuccess) {
         delete h;
         return fail(WN_ERR_CUDA, "cudaMalloc failed");
@@ -665,8 +943,9 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
 int32_t wn_destroy(void* handle) {
     WnHandle* h = (WnHandle*)handle;
     if (!h) return WN_OK;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
+    cudaFree(h->d_bpack); cudaFree(h->d_passes);
     cudaFree(h->d_wpack); cudaFree(h->d_cwpack); cudaFree(h->d_wg); cudaFree(h->d_first_w); cudaFree(h->d_first_b);
     cudaFree(h->d_ringtab); cudaFree(h->d_err); cudaFree(h->d_xbuf); cudaFree(h->d_ring); cudaFree(h->d_gbias);
     cudaFree(h->d_scratch);
@@ -680,8 +959,7 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
     if (!h) return fail(WN_ERR_INVALID, "null handle");
     int32_t rc = check_weights(h->cfg, w);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const WnPlan& pl = h->base;
+    DeviceGuard guard(h->cfg.device);
     const wn_config& c = h->cfg;
     auto upload = [&](float** dst, const std::vector<float>& src) -> int32_t {
         if (*dst) cudaFree(*dst);
@@ -690,17 +968,42 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
         if (!src.empty()) CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
         return WN_OK;
     };
-    std::vector<float> img((size_t)pl.P * pl.cta_w_floats);
-    {
+    struct Shape { int L, G, R, G2, kw, O, P; } pl;
+    if (h->engine == 6) {
+        const Wn6Plan& p6 = h->base6;
+        pl = {p6.L, p6.G, p6.R, p6.G2, p6.kw, p6.O, p6.P};
         Folded fo;
-        fold_layers(pl, *w, fo);
-        for (int p = 0; p < pl.P; ++p) pack_cta(pl, *w, fo, p, img.data() + (size_t)p * pl.cta_w_floats);
+        fold_layers(pl.L, pl.G, pl.R, pl.G2, pl.kw, *w, fo);
+        std::vector<float> img((size_t)p6.P * p6.cta_w_floats), cw((size_t)p6.P * p6.cta_cw_floats),
+            bs((size_t)p6.P * p6.cta_b_floats);
+        for (int p = 0; p < p6.P; ++p) {
+            pack6_cta(p6, h->passes6, *w, fo, p, img.data() + (size_t)p * p6.cta_w_floats);
+            pack6_cw(p6, *w, p, cw.data() + (size_t)p * p6.cta_cw_floats);
+            pack6_bias(p6, *w, fo, p, bs.data() + (size_t)p * p6.cta_b_floats);
+        }
+        if ((rc = upload(&h->d_wpack, img))) return rc;
+        h->wpack_bytes = img.size() * sizeof(float);
+        if ((rc = upload(&h->d_cwpack, cw))) return rc;
+        if ((rc = upload(&h->d_bpack, bs))) return rc;
+        if (h->d_passes) cudaFree(h->d_passes);
+        h->d_passes = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&h->d_passes, std::max<size_t>(16, h->passes6.size() * sizeof(Wn6Pass))));
+        CUDA_TRY(cudaMemcpy(h->d_passes, h->passes6.data(), h->passes6.size() * sizeof(Wn6Pass), cudaMemcpyHostToDevice));
+    } else {
+        const WnPlan& p5 = h->base;
+        pl = {p5.L, p5.G, p5.R, p5.G2, p5.kw, p5.O, p5.P};
+        std::vector<float> img((size_t)p5.P * p5.cta_w_floats);
+        {
+            Folded fo;
+            fold_layers(pl.L, pl.G, pl.R, pl.G2, pl.kw, *w, fo);
+            for (int p = 0; p < p5.P; ++p) pack_cta(p5, *w, fo, p, img.data() + (size_t)p * p5.cta_w_floats);
+        }
+        if ((rc = upload(&h->d_wpack, img))) return rc;
+        h->wpack_bytes = img.size() * sizeof(float);
+        std::vector<float> cw((size_t)p5.P * p5.cta_cw_floats);
+        for (int p = 0; p < p5.P; ++p) pack_cw_cta(p5, *w, p, cw.data() + (size_t)p * p5.cta_cw_floats);
+        if ((rc = upload(&h->d_cwpack, cw))) return rc;
     }
-    if ((rc = upload(&h->d_wpack, img))) return rc;
-    h->wpack_bytes = img.size() * sizeof(float);
-    std::vector<float> cw((size_t)pl.P * pl.cta_cw_floats);
-    for (int p = 0; p < pl.P; ++p) pack_cw_cta(pl, *w, p, cw.data() + (size_t)p * pl.cta_cw_floats);
-    if ((rc = upload(&h->d_cwpack, cw))) return rc;
     std::vector<float> wg;
     if (c.gin_channels > 0) {
         wg.resize((size_t)pl.L * pl.G * c.gin_channels);
@@ -748,7 +1051,12 @@ static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
         if (quant && !a->out_index) return fail(WN_ERR_INVALID, "out_index required with QUANTIZE");
         if (!quant && !a->out_dense) return fail(WN_ERR_INVALID, "out_dense required without QUANTIZE");
         if (a->T_test > 0 && !a->test_index && !a->test_dense) return fail(WN_ERR_INVALID, "test_index or test_dense required when T_test > 0");
-        if (a->initial_index >= c.out_channels) return fail(WN_ERR_INVALID, "initial_index out of range");
+        // the reference's default start class is 127 (wavenet.py:286) and indexing a smaller model with it raises
+        const int start = a->initial_index < 0 ? 127 : a->initial_index;
+        if (a->T_test == 0 && !a->initial_rows && !a->initial_dense && start >= c.out_channels)
+            return fail(WN_ERR_INVALID, "initial_index out of range (the default start class is 127, wavenet.py:286)");
+        if ((a->initial_rows || a->initial_dense) && h->engine != 6)
+            return fail(WN_ERR_INVALID, "per-utterance initial inputs need the cluster engine");
     }
     if (a->noise_kind == WN_NOISE_REPLAY) {
         const bool quant = (a->flags & WN_FLAG_QUANTIZE) != 0;
@@ -767,14 +1075,13 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
     if (!h->have_weights) return fail(WN_ERR_STATE, "wn_generate before wn_load_weights");
     int32_t rc = validate_args(h, a);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)a->stream;
-    // batch tiles: 8 utterances per launch spill registers in this build (168/thread with 10 warps), so
-    // the default tile is 4 (measured faster per utterance, profiles/r1_*sweep*); WN_MAX_TILE=8 overrides
-    const int tile = std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)));
+    // batch tiles: up to 8 utterances share one launch (one pass over the weights per step for all of them)
+    const int tile = max_tile(h->engine);
     for (int b0 = 0; b0 < a->B; b0 += tile) {
         const int Bc = std::min(tile, a->B - b0);
-        rc = launch_chunk(h, a, b0, Bc, st);
+        rc = h->engine == 6 ? launch_chunk6(h, a, b0, Bc, st) : launch_chunk(h, a, b0, Bc, st);
         if (rc) return rc;
     }
     h->last_stream = st;
@@ -785,7 +1092,7 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
 int32_t wn_sync(void* handle) {
     WnHandle* h = (WnHandle*)handle;
     if (!h) return fail(WN_ERR_INVALID, "null handle");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     CUDA_TRY(cudaStreamSynchronize(h->last_stream));
     h->pending = false;
     int err[4] = {0, 0, 0, 0};
@@ -793,9 +1100,13 @@ int32_t wn_sync(void* handle) {
     if (h->d_prof && env_int("WN_PROF", 0)) {
         std::vector<long long> pc(h->prof_bytes / sizeof(long long));
         CUDA_TRY(cudaMemcpy(pc.data(), h->d_prof, h->prof_bytes, cudaMemcpyDeviceToHost));
-        const char* names[16] = {"C.poll", "C.gemv", "C.barrier", "C.finalize+publish", "C.acquire+pre", "C.head",
-                                 "C.sample+sync", "C.x0", "D.wait_stash", "D.gemv", "D.finalize", "D.sample+sync",
-                                 "-", "-", "-", "-"};
+        const char* names5[16] = {"C.poll", "C.gemv", "C.barrier", "C.finalize+publish", "C.acquire+pre", "C.head",
+                                  "C.sample+sync", "C.x0", "D.wait_stash", "D.gemv", "D.finalize", "D.sample+sync",
+                                  "-", "-", "-", "-"};
+        const char* names6[16] = {"F0.wait_partials", "F0.finalise+publish", "-", "-", "-", "-", "-", "-",
+                                  "W0.acquire_blob", "W0.wait_input", "W0.critical_passes", "W0.deferred+release",
+                                  "-", "-", "-", "-"};
+        const char** names = h->engine == 6 ? names6 : names5;
         const int P = (int)(pc.size() / 16);
         for (int i = 0; i < 12; ++i) {
             long long mn = pc[i], mx = pc[i], sum = 0;
@@ -816,12 +1127,24 @@ int32_t wn_sync(void* handle) {
 int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out) {
     WnHandle* h = (WnHandle*)handle;
     if (!h || !out) return fail(WN_ERR_INVALID, "null argument");
+    const int bt = std::min(std::max(batch, 1), max_tile(h->engine));
+    if (h->engine == 6) {
+        Wn6Plan pl6;
+        std::vector<Wn6Pass> ps;
+        std::vector<int> rt6;
+        int32_t rc6 = build_plan6(h->cfg, bt, h->num_sms, h->smem_cap, h->max_clusters, pl6, ps, rt6);
+        if (rc6) return rc6;
+        fill_info6(h->cfg, pl6, out);
+        out->launches = h->launches;
+        return WN_OK;
+    }
     WnPlan pl;
     std::vector<int> rt;
-    int32_t rc = build_plan(h->cfg, std::min(batch, std::max(1, std::min(WN_MAX_BT, env_int("WN_MAX_TILE", 4)))), h->num_sms, h->smem_cap, pl, rt);
+    int32_t rc = build_plan(h->cfg, bt, h->num_sms, h->smem_cap, pl, rt);
     if (rc) return rc;
     fill_info(h->cfg, pl, out);
     out->launches = h->launches;
+    out->engine = 5;
     return WN_OK;
 }
 
@@ -832,7 +1155,7 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
     if (!h->have_weights) return fail(WN_ERR_STATE, "wn_generate_host before wn_load_weights");
     int32_t rc = validate_args(h, a);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h->cfg.device);
     const wn_config& c = h->cfg;
     const size_t B = a->B, T = a->T, O = c.out_channels, Tt = a->T_test;
     const size_t K = (c.head_kind == WN_HEAD_SOFTMAX) ? 0 : (O == 2 ? 1 : O / 3);
@@ -849,6 +1172,8 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
     const size_t o_c = add(in, a->c, nullptr, B * T * (size_t)c.cin_channels * 4);
     const size_t o_g = add(in, a->g, nullptr, B * (size_t)c.gin_channels * 4);
     const size_t o_init = add(in, a->initial, nullptr, B * 4);
+    const size_t o_irow = add(in, a->initial_rows, nullptr, B * 4);
+    const size_t o_iden = add(in, a->initial_dense, nullptr, B * O * 4);
     const size_t o_ts = add(in, a->test_scalar, nullptr, B * Tt * 4);
     const size_t o_ti = add(in, a->test_index, nullptr, B * Tt * 4);
     const size_t o_td = add(in, a->test_dense, nullptr, B * Tt * O * 4);
@@ -870,6 +1195,8 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
     d.c = (const float*)dp(o_c);
     d.g = (const float*)dp(o_g);
     d.initial = (const float*)dp(o_init);
+    d.initial_rows = (const int32_t*)dp(o_irow);
+    d.initial_dense = (const float*)dp(o_iden);
     d.test_scalar = (const float*)dp(o_ts);
     d.test_index = (const int32_t*)dp(o_ti);
     d.test_dense = (const float*)dp(o_td);

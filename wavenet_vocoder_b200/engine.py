@@ -153,7 +153,8 @@ class SynthesisEngine:
     # ------------------------------------------------------------------ one synthesis call
     def generate(self, *, B: int, T: int, c: Optional[torch.Tensor] = None,
                  g: Optional[torch.Tensor] = None, initial: Optional[torch.Tensor] = None,
-                 initial_index: int = -1, test_scalar: Optional[torch.Tensor] = None,
+                 initial_index: int = -1, initial_rows: Optional[torch.Tensor] = None,
+                 initial_dense: Optional[torch.Tensor] = None, test_scalar: Optional[torch.Tensor] = None,
                  test_index: Optional[torch.Tensor] = None,
                  test_dense: Optional[torch.Tensor] = None, softmax=True, quantize=True,
                  noise: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None,
@@ -179,6 +180,8 @@ class SynthesisEngine:
         a.g = dptr(g, shape=(B, self.gin) if g is not None else None)
         a.initial = dptr(initial, shape=(B,) if initial is not None else None)
         a.initial_index = int(initial_index)
+        a.initial_rows = dptr(initial_rows, torch.int32, shape=(B,) if initial_rows is not None else None)
+        a.initial_dense = dptr(initial_dense, shape=(B, O) if initial_dense is not None else None)
         T_test = 0
         if test_scalar is not None:
             T_test = test_scalar.size(1)

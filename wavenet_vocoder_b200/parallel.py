@@ -30,13 +30,21 @@ def tile_batches(indices: Sequence[int], lengths: Sequence[int], tile: int) -> L
     return [idx[k:k + tile] for k in range(0, len(idx), tile)]
 
 
-def gather_waveforms(local: Dict[int, torch.Tensor], n_total: int, dst: int = 0, group=None):
+def gather_waveforms(local: Dict[int, torch.Tensor], n_total: int, dst: int = 0, group=None, device=None):
     """Collect {utterance index: 1-D waveform} from every rank on ``dst`` (list indexed by utterance,
-    None elsewhere).  Tensors are gathered as one padded block per rank (NCCL or gloo)."""
+    None elsewhere).  Tensors are gathered as one padded block per rank (NCCL or gloo).  Every rank must
+    use the same device type even when it holds no utterance: ``device`` defaults to the current CUDA
+    device under the NCCL backend and to the CPU otherwise."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    dev = next(iter(local.values())).device if local else torch.device("cpu")
+    if device is None:
+        if dist.get_backend(group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            device = torch.device("cpu")
+    dev = torch.device(device)
+    local = {i: v.to(dev) for i, v in local.items()}
     meta = torch.tensor([len(local), max([v.numel() for v in local.values()], default=0)], device=dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)

@@ -128,8 +128,44 @@ class WaveNet(nn.Module):
 
     # ------------------------------------------------------------------ engine management
     def _param_version(self):
-        dev = next(self.parameters()).device
-        return (str(dev),) + tuple((id(p), p._version) for p in self.parameters())
+        """Key of the packed-weight cache: identity and in-place version of every parameter plus a
+        data-dependent fingerprint (one fused norm over all parameters), so that updates through
+        ``p.data.copy_()`` / ``p.data = ...`` (EMA swaps, weight surgery), which do not bump ``_version``,
+        are seen too."""
+        params = list(self.parameters())
+        dev = params[0].device
+        norms = torch.stack(torch._foreach_norm([p.detach() for p in params])).double()
+        sums = torch.stack([p.detach().reshape(-1)[0] for p in params]).double()
+        finger = torch.cat([norms, sums]).cpu().numpy().tobytes()
+        return (str(dev), finger) + tuple((id(p), p._version) for p in params)
+
+    def invalidate_engine(self):
+        """Forget the packed weights (they are rebuilt by the next incremental_forward)."""
+        self._engine_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self._engine_key = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._engine_key = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        # the engine holds ctypes handles and device buffers: never pickled / deep-copied with the module
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_key"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_engine", "_engine_key") else copy.deepcopy(v, memo)
+        return new
 
     def _get_engine(self) -> SynthesisEngine:
         dev = next(self.parameters()).device
@@ -219,33 +255,46 @@ class WaveNet(nn.Module):
             assert c.size(1) == T and c.size(2) == self.cin_channels
         initial = None
         initial_index = -1
-        if initial_input is not None:
+        initial_rows = initial_dense = None
+        if initial_input is not None and test_inputs is None:      # test_inputs override step 0 (wavenet.py:299-301)
             ii = initial_input.to(dev).float()
             if self.scalar_input:
                 initial = ii.reshape(ii.size(0), -1)[:, 0].contiguous()
-                if c is None and test_inputs is None and g is None:
+                if c is None and g is None:
                     B = initial.size(0)            # nothing else defines the batch (the reference assumes B=1 here)
                 if initial.size(0) == 1 and B > 1:
                     initial = initial.expand(B).contiguous()
                 if initial.size(0) != B:
                     raise ValueError("initial_input has %d rows but the batch is %d" % (initial.size(0), B))
             else:
-                if ii.size(1) == O:
+                if ii.size(1) == O and ii.size(-1) != O:
                     ii = ii.transpose(1, 2)
-                first = ii.reshape(ii.size(0), -1, O)[:, 0]
+                first = ii.reshape(ii.size(0), -1, O)[:, 0]                           # (B0, O), fed as is (wavenet.py:281-292)
+                if c is None and g is None:
+                    B = first.size(0)
+                if first.size(0) == 1 and B > 1:
+                    first = first.expand(B, -1)
+                if first.size(0) != B:
+                    raise ValueError("initial_input has %d rows but the batch is %d" % (first.size(0), B))
                 idx = first.argmax(-1)
-                if int((idx != idx[0]).any()):
-                    raise ValueError("per-utterance one-hot initial inputs are not supported; "
-                                     "use test_inputs for the first step")
-                initial_index = int(idx[0])
+                onehot = torch.zeros_like(first).scatter_(-1, idx.unsqueeze(-1), 1.0)
+                if torch.equal(onehot, first):
+                    initial_rows = idx.to(torch.int32).contiguous()
+                else:
+                    initial_dense = first.contiguous()
         out, params = eng.generate(
             B=B, T=T, c=c, g=g_vec, initial=initial, initial_index=initial_index,
+            initial_rows=initial_rows, initial_dense=initial_dense,
             test_scalar=test_scalar, test_index=test_index, test_dense=test_dense,
             softmax=bool(softmax), quantize=bool(quantize), noise=noise, seed=seed,
             want_params=return_params, sync=False)
-        for _ in tqdm(range(T)):          # progress-bar compatibility; the samples are already in flight
-            pass
+        # progress-bar compatibility in O(1): the T steps are one kernel launch already in flight
+        bar = tqdm(range(T))
         eng.sync()
+        if hasattr(bar, "update"):
+            bar.update(T)
+        if hasattr(bar, "close"):
+            bar.close()
         if self.scalar_input:
             y = out.view(B, 1, T)
         elif quantize:
