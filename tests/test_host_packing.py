@@ -168,10 +168,12 @@ class PackedModel:
         return self.img[p]["w"][off:off + n]
 
     def run_stage(self, kind, stage, xin):
-        """xin[r]: the K-slice of rank r (values).  Returns (crit, defer): [P][row][src rank] partial sums."""
+        """xin[r]: the K-slice of rank r (values).  Returns the partial sums [P][row][src rank] sent to the three
+        finaliser warps of every owner: (F0: gate / skip / head rows, DF: deferred rows, F1: residual rows)."""
         pl = self.pl
         crit = np.zeros((pl.P, pl.nrow_c, pl.CS), np.float32)
         defer = np.zeros((pl.P, pl.nrow_d, pl.CS), np.float32)
+        resid = np.zeros((pl.P, max(pl.nrow_x, 1), pl.CS), np.float32)
         for p in range(pl.P):
             c, r = divmod(p, pl.CS)
             blob = self.blob(p, stage)
@@ -186,9 +188,9 @@ class PackedModel:
                             continue
                         ks = ps.x_off + np.arange(16)[None, :] + 16 * np.arange(ps.nit)[:, None]       # (nit, 16)
                         sums = np.einsum("jsi,js->i", tile[:, g * 16:(g + 1) * 16, :].astype(np.float64), x[ks].astype(np.float64))
-                        dst = defer if ps.deferred else crit
+                        dst = (crit, defer, resid)[ps.dst]
                         dst[c * pl.CS + ps.owner[g], ps.dst_row[g]:ps.dst_row[g] + 4, r] = sums.astype(np.float32)
-        return crit, defer
+        return crit, defer, resid
 
     def run_teacher_forced(self, b):
         gc, pl, L, kw = self.gc, self.pl, self.L, self.kw
@@ -243,7 +245,7 @@ class PackedModel:
                     xin = slices([(ypub, my), (xpub, mx)])
                     for r in range(CS):
                         assert len(xin[r]) == pl.Ky + pl.Kx
-                crit, defer = self.run_stage(kind, s_, xin)
+                crit, defer, resid = self.run_stage(kind, s_, xin)
                 ynew = np.zeros((P, my), np.float32)
                 xnew = np.zeros((P, mx), np.float32)
                 for p in range(P):
@@ -266,7 +268,7 @@ class PackedModel:
                         ynew[p, j] = np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))
                     if s_ >= 1:
                         x0r, nx = own(R, NC, CS, c, r)
-                        o = crit[p, 4 * qA:4 * qA + mx].sum(axis=1) + bias[pl.bo_xb + s_ * 4 * qB: pl.bo_xb + s_ * 4 * qB + mx]
+                        o = resid[p, :mx].sum(axis=1) + bias[pl.bo_xb + s_ * 4 * qB: pl.bo_xb + s_ * 4 * qB + mx]
                         xnew[p, :nx] = ((o + xpub[p]) * rs2)[:nx]
                         layer = s_ - 1
                         for tap in range(kw - 1):
@@ -279,7 +281,7 @@ class PackedModel:
                     xpub = xnew
             # stage L: skip of the last layer
             xin = slices([(ypub, my), (xpub, mx)])
-            crit, defer = self.run_stage(K_TAIL, L, xin)
+            crit, defer, _ = self.run_stage(K_TAIL, L, xin)
             skpub = np.zeros((P, ms), np.float32)
             for p in range(P):
                 c, r = divmod(p, CS)
@@ -291,13 +293,13 @@ class PackedModel:
                 for tap in range(kw - 1):
                     D = (kw - 1 - tap) * dil[L - 1]
                     rings[p][L - 1][tap][t % D] = defer[p, tap * 2 * my:(tap + 1) * 2 * my].sum(axis=1)
-            crit, _ = self.run_stage(K_HEAD1, L + 1, slices([(skpub, ms)]))
+            crit, _, _ = self.run_stage(K_HEAD1, L + 1, slices([(skpub, ms)]))
             h1pub = np.zeros((P, ms), np.float32)
             for p in range(P):
                 c, r = divmod(p, CS)
                 a0, na = own(S, NC, CS, c, r)
                 h1pub[p, :na] = np.maximum(crit[p, :ms].sum(axis=1) + self.img[p]["b"][pl.bo_ha:pl.bo_ha + ms], 0)[:na]
-            crit, _ = self.run_stage(K_HEAD2, L + 2, slices([(h1pub, ms)]))
+            crit, _, _ = self.run_stage(K_HEAD2, L + 2, slices([(h1pub, ms)]))
             for p in range(P):
                 c, r = divmod(p, CS)
                 b0, nb = own(O, NC, CS, c, r)
@@ -334,16 +336,18 @@ def test_pass_lists_cover_every_row_once():
             for wv in range(8):
                 b0, n, nc = pl.pass_begin[kind][wv], pl.pass_count[kind][wv], pl.pass_crit[kind][wv]
                 for i, ps in enumerate(passes[b0:b0 + n]):
-                    assert (ps.deferred == 0) == (i < nc)
+                    assert (ps.dst != 1) == (i < nc)
                     spans.append((ps.w_off, ps.w_off + ps.nit * 128))
                     for g in range(2):
                         if ps.owner[g] >= 0:
-                            key = (ps.deferred, ps.owner[g], ps.dst_row[g])
+                            key = (ps.dst, ps.owner[g], ps.dst_row[g])
                             assert key not in seen
                             seen[key] = ps.job
             rows_c = {(o, r) for (d, o, r) in seen if d == 0}
             rows_d = {(o, r) for (d, o, r) in seen if d == 1}
+            rows_x = {(o, r) for (d, o, r) in seen if d == 2}
             assert len(rows_c) * 4 == pl.rows_c[kind] * pl.CS and len(rows_d) * 4 == pl.rows_d[kind] * pl.CS
+            assert len(rows_x) * 4 == (pl.rows_x * pl.CS if kind == K_LAYER else 0)
             if kind in (K_FIRST, K_LAYER):
                 spans.sort()
                 assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))

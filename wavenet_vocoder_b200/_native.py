@@ -78,7 +78,7 @@ class wn_plan_info(C.Structure):
 class Wn6Pass(C.Structure):
     """Mirror of struct Wn6Pass (csrc/wn6_plan.h): one warp pass = two row quads x nit k-steps."""
     _fields_ = [("w_off", C.c_int32), ("nit", C.c_int16), ("x_off", C.c_int16), ("dst_row", C.c_int16 * 2),
-                ("owner", C.c_int8 * 2), ("deferred", C.c_int8), ("job", C.c_int8), ("quad", C.c_int16 * 2)]
+                ("owner", C.c_int8 * 2), ("dst", C.c_int8), ("job", C.c_int8), ("quad", C.c_int16 * 2)]
 
 
 _NKIND, _NCW = 5, 8
@@ -91,8 +91,8 @@ class Wn6Plan(C.Structure):
                 [(n, C.c_int32) for n in ("NC", "CS", "P", "BT", "my", "mx", "ms", "mo", "qA", "qB", "qD", "qS", "qHA",
                                           "qHB", "Ky", "Kx", "Ksk", "Kh2", "xin_vals", "NS", "rs_yx", "rs_sk", "rs_h2")] +
                 [(n, C.c_int64) for n in ("ex_yx", "ex_sk", "ex_h1", "ex_h2", "ex_pairs")] +
-                [("nrow_c", C.c_int32), ("nrow_d", C.c_int32), ("rows_c", C.c_int32 * _NKIND),
-                 ("rows_d", C.c_int32 * _NKIND), ("npass", C.c_int32),
+                [("nrow_c", C.c_int32), ("nrow_d", C.c_int32), ("nrow_x", C.c_int32), ("rows_c", C.c_int32 * _NKIND),
+                 ("rows_d", C.c_int32 * _NKIND), ("rows_x", C.c_int32), ("npass", C.c_int32),
                  ("pass_begin", (C.c_int32 * _NCW) * _NKIND), ("pass_count", (C.c_int32 * _NCW) * _NKIND),
                  ("pass_crit", (C.c_int32 * _NCW) * _NKIND)] +
                 [(n, C.c_int32) for n in ("fb_floats", "lb_floats", "tb_floats", "slot_floats")] +
@@ -100,7 +100,7 @@ class Wn6Plan(C.Structure):
                 [(n, C.c_int32) for n in ("nblobs", "nres", "nring", "bo_zb", "bo_xb", "bo_sb", "bo_ha", "bo_hb",
                                           "cta_b_floats")] +
                 [("cta_cw_floats", C.c_int64), ("ring_in_smem", C.c_int32), ("ring_pos_total", C.c_int64)] +
-                [(n, C.c_int32) for n in ("sm_bar", "sm_misc", "sm_pass", "sm_ringtab", "sm_xin", "sm_part", "sm_dpart",
+                [(n, C.c_int32) for n in ("sm_bar", "sm_misc", "sm_pass", "sm_ringtab", "sm_xin", "sm_part", "sm_dpart", "sm_partx",
                                           "sm_sb", "sm_pre", "sm_cond", "sm_bias", "sm_skipacc", "sm_xown", "sm_hs",
                                           "sm_noise", "sm_in", "sm_x0w", "sm_ring", "sm_slots", "smem_bytes")])
 

@@ -15,7 +15,7 @@ static int default_max_clusters(int num_sms, int cs) {
 }
 
 struct JobSpec {
-    int job, quads_per_owner, x_off, klen, deferred, row_base;
+    int job, quads_per_owner, x_off, klen, dst, row_base;
 };
 
 static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long smem_cap, int max_clusters_hint,
@@ -106,7 +106,9 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
 
     // ---- partial buffers
     pl.rows_c[WN6_K_FIRST] = 4 * pl.qA;
-    pl.rows_c[WN6_K_LAYER] = 4 * pl.qA + 4 * pl.qB;
+    pl.rows_c[WN6_K_LAYER] = 4 * pl.qA;
+    pl.rows_x = 4 * pl.qB;
+    pl.nrow_x = 4 * pl.qB;
     pl.rows_c[WN6_K_TAIL] = 4 * pl.qS;
     pl.rows_c[WN6_K_HEAD1] = 4 * pl.qHA;
     pl.rows_c[WN6_K_HEAD2] = 4 * pl.qHB;
@@ -124,7 +126,7 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
     std::vector<std::vector<JobSpec>> kinds(WN6_NKIND);
     kinds[WN6_K_FIRST] = {{WN6_J_A0, pl.qA, Ky, Kx, 0, 0}};
     kinds[WN6_K_LAYER] = {{WN6_J_A, pl.qA, 0, Ky + Kx, 0, 0},
-                          {WN6_J_B, pl.qB, 0, Ky, 0, 4 * pl.qA},
+                          {WN6_J_B, pl.qB, 0, Ky, 2, 0},
                           {WN6_J_D, pl.qD, Ky, Kx, 1, 0},
                           {WN6_J_S, pl.qS, 0, Ky, 1, 4 * pl.qD}};
     kinds[WN6_K_TAIL] = {{WN6_J_S, pl.qS, 0, Ky, 0, 0}, {WN6_J_D, pl.qD, Ky, Kx, 1, 0}};
@@ -148,7 +150,7 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
                 memset(&ps, 0, sizeof(ps));
                 ps.nit = (int16_t)nit;
                 ps.x_off = (int16_t)js.x_off;
-                ps.deferred = (int8_t)js.deferred;
+                ps.dst = (int8_t)js.dst;
                 ps.job = (int8_t)js.job;
                 for (int g = 0; g < 2; ++g) {
                     const int qq = q + g;
@@ -165,7 +167,7 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
                 const int w = rr % WN6_NCW;
                 ++rr;
                 per_warp[w].push_back(ps);
-                if (!js.deferred) ncrit[w] = (int)per_warp[w].size();
+                if (js.dst != 1) ncrit[w] = (int)per_warp[w].size();
             }
         }
         // a warp's critical passes must precede its deferred ones (jobs are listed in that order already)
@@ -233,7 +235,7 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
             return (int)r;
         };
         const long long tab = (long long)pl.L * 4 * pl.qA * BT * 4;
-        pl.sm_bar = take((long long)(2 * pl.nblobs + 16) * 8, 16);
+        pl.sm_bar = take((long long)(2 * pl.nblobs + 24) * 8, 16);
         pl.sm_misc = take(16, 16);
         pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
         pl.sm_pass = take((long long)pl.npass * (long long)sizeof(Wn6Pass), 16);
@@ -241,6 +243,7 @@ static int32_t build_plan6(const wn_config& c, int batch, int num_sms, long long
         pl.sm_xin = take(2LL * pl.xin_vals * BT * 4, 16);
         pl.sm_part = take(2LL * pl.nrow_c * CS * BT * 4, 16);
         pl.sm_dpart = take(2LL * pl.nrow_d * CS * BT * 4, 16);
+        pl.sm_partx = take(2LL * pl.nrow_x * CS * BT * 4, 16);
         pl.sm_sb = take(tab, 16);
         pl.sm_pre = take(tab, 16);
         pl.sm_cond = take(pl.C > 0 ? 2 * tab : 16, 16);

@@ -136,6 +136,10 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t raddr, float v0, float v
                  "r"(__float_as_uint(v0)), "r"(__float_as_uint(v1)), "r"(rbar)
                  : "memory");
 }
+// arrive on an mbarrier of another block of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
@@ -226,12 +230,13 @@ struct Engine {
     const Wn6Ptrs& pp;
     unsigned char* sm;
     int tid, warp, lane, p, c, rank;
-    uint64_t *bar_full, *bar_empty, *bar_cfull, *bar_cempty, *bar_in, *bar_free, *bar_part, *bar_dpart, *bar_pre;
+    uint64_t *bar_full, *bar_empty, *bar_cfull, *bar_cempty, *bar_in, *bar_free, *bar_part, *bar_dpart, *bar_partx,
+        *bar_dfree, *bar_pre, *bar_x0, *bar_ps;
     volatile int* s_abort;
     volatile int* s_ddone;         // deferred stages completed by DF (monotonic)
     Wn6Pass* passes;
     int* ringtab;                  // [e][3]: offset, delay, t mod delay
-    float *xin, *part, *dpart, *sb, *pre, *cond, *bias, *skipacc, *xown, *x0own, *hs, *noise, *x0w, *slots;
+    float *xin, *part, *dpart, *partx, *sb, *pre, *cond, *bias, *skipacc, *xown, *x0own, *hs, *noise, *x0w, *slots;
     int* h2map;
     volatile float* ring;
     float* s_in;      // [BT] scalar feedback
@@ -255,7 +260,11 @@ struct Engine {
         bar_free = bar_in + 2;
         bar_part = bar_free + 2;
         bar_dpart = bar_part + 2;
-        bar_pre = bar_dpart + 2;
+        bar_partx = bar_dpart + 2;
+        bar_dfree = bar_partx + 2;
+        bar_pre = bar_dfree + 2;
+        bar_x0 = bar_pre + 1;
+        bar_ps = bar_x0 + 1;
         s_abort = reinterpret_cast<volatile int*>(sm + pl.sm_misc);
         s_ddone = s_abort + 1;
         passes = reinterpret_cast<Wn6Pass*>(sm + pl.sm_pass);
@@ -263,6 +272,7 @@ struct Engine {
         xin = reinterpret_cast<float*>(sm + pl.sm_xin);
         part = reinterpret_cast<float*>(sm + pl.sm_part);
         dpart = reinterpret_cast<float*>(sm + pl.sm_dpart);
+        partx = reinterpret_cast<float*>(sm + pl.sm_partx);
         sb = reinterpret_cast<float*>(sm + pl.sm_sb);
         pre = reinterpret_cast<float*>(sm + pl.sm_pre);
         cond = reinterpret_cast<float*>(sm + pl.sm_cond);
@@ -289,9 +299,28 @@ struct Engine {
     __device__ __forceinline__ bool check_abort(uint32_t what, long long& t0) {
         return check_abort_slow(s_abort, pp.err, pp.timeout_cycles, what, p, t0);
     }
-    // `relaxed` waits (anything off the critical path) back off with nanosleep
+    // Waits are WARP-COLLECTIVE (all 32 lanes call them together) and return a warp-uniform verdict, so that a
+    // watchdog abort never leaves some lanes of a warp behind in a later shuffle or vote.  `relaxed` waits
+    // (anything off the critical path) back off with nanosleep.
     template <bool relaxed = false>
     __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, uint32_t what) {
+        if (!dead) {
+            uint32_t spins = 0;
+            long long t0 = 0;
+            while (!mbar_try_wait(bar, parity)) {
+                if (relaxed) __nanosleep(64);
+                if (((++spins) & (relaxed ? 63u : 255u)) == 0 && check_abort(what, t0)) {
+                    dead = true;
+                    break;
+                }
+            }
+        }
+        dead = __any_sync(0xffffffffu, dead);
+        return !dead;
+    }
+    // single-lane variant (the TMA lane)
+    template <bool relaxed = false>
+    __device__ __forceinline__ bool wait_bar_lane(uint64_t* bar, uint32_t parity, uint32_t what) {
         if (dead) return false;
         uint32_t spins = 0;
         long long t0 = 0;
@@ -305,16 +334,25 @@ struct Engine {
         return true;
     }
     __device__ __forceinline__ void wait_count(volatile int* cnt, int need, uint32_t what) {
-        if (dead) return;
-        uint32_t spins = 0;
-        long long t0 = 0;
-        while (*cnt < need) {
-            if (((++spins) & 255u) == 0 && check_abort(what, t0)) {
-                dead = true;
-                return;
+        if (!dead) {
+            uint32_t spins = 0;
+            long long t0 = 0;
+            while (*cnt < need) {
+                if (((++spins) & 255u) == 0 && check_abort(what, t0)) {
+                    dead = true;
+                    break;
+                }
             }
+            __threadfence_block();
         }
-        __threadfence_block();
+        dead = __any_sync(0xffffffffu, dead);
+    }
+    // barrier over the polling warps with a watchdog (a plain bar.sync would hang if one of them aborted)
+    uint32_t ps_par = 0;
+    __device__ __forceinline__ void poller_sync() {
+        if (!dead) mbar_arrive(bar_ps);
+        wait_bar(bar_ps, ps_par, 0x00200000u);
+        ps_par ^= 1u;
     }
     __device__ __forceinline__ void publish(long long pair, float v, uint32_t tag) { st_pair(pp.xbuf + pair, v, tag); }
 
@@ -336,7 +374,7 @@ struct Engine {
         uint32_t s = 0, u = 0;
         for (uint32_t js = 0; js < total; ++js) {
             if (u > 0) {
-                if (!wait_bar<true>(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
+                if (!wait_bar_lane<true>(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
             }
             const uint32_t bytes = (uint32_t)wn6_blob_floats(pl, i) * 4u;
             uint64_t* fb = &bar_full[pl.nres + s];
@@ -612,9 +650,10 @@ struct Engine {
                 if (bad == 0) break;
                 if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                     dead = true;
-                    return;
+                    break;
                 }
             }
+            if (dead) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u * NPL;
@@ -624,6 +663,7 @@ struct Engine {
                 }
             }
         }
+        dead = __any_sync(0xffffffffu, dead);
     }
     // x_0 = first 1x1 conv of the fed-back sample (wavenet.py:308) at the block's K-slice -> dst[k][b], k < Kx,
     // and at the rows the block owns -> x0own
@@ -676,6 +716,7 @@ struct Engine {
                     break;
                 }
             }
+            if (dead) break;
             const int e0 = rr * nsl + 2 * jj;
             const int m0 = h2map[e0];
             if (m0 >= 0) hs[m0] = __uint_as_float(q.x);
@@ -684,20 +725,25 @@ struct Engine {
                 if (m1 >= 0) hs[m1] = __uint_as_float(q.z);
             }
         }
-        bar_sync_n<2, NPL>();
+        dead = __any_sync(0xffffffffu, dead);
+        poller_sync();
+        if (dead) return;
         if (p == 0 && pp.params_out != nullptr) {
             const int O = pl.O, T = pp.T;
             for (int i = pl_; i < O * BT; i += NPL) {
                 const int o = i / BT, b = i % BT;
                 if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
             }
-            if (pl.head_kind == 2) bar_sync_n<2, NPL>();     // the softmax sampler overwrites hs in place
+            if (pl.head_kind == 2) {                         // the softmax sampler overwrites hs in place
+                poller_sync();
+                if (dead) return;
+            }
         }
         for (int b = warp; b < BT; b += WN6_NPW) {
             sample_utt(t, b);
             if (t + 1 < pp.T) fetch_noise(t + 1, b);
         }
-        bar_sync_n<2, NPL>();
+        poller_sync();
     }
 
     __device__ void poll_loop() {
@@ -713,8 +759,9 @@ struct Engine {
                 float* xb = xin + (size_t)par * xin_floats;
                 if (s == 0) {
                     if (t > 0) read_head_and_sample(t - 1, pl_);
-                    if (dead || *s_abort) { dead = true; break; }
+                    if (dead) break;
                     write_x0(xb + pl.Ky * BT, pl_, true);
+                    mbar_arrive(bar_x0);          // x_0 at the rows this block owns is in place (read by F1 in stage 1)
                 } else {
                     int npairs;
                     if (s == 1) npairs = pl.Ky * BT;                       // x_0 is evaluated locally
@@ -757,7 +804,7 @@ struct Engine {
 
     // one pass: two row quads (lane groups) x nit k-steps, then the partial sums go to the row owners
     __device__ __forceinline__ void run_pass(const Wn6Pass& ps, const float* __restrict__ blob, const float* __restrict__ xb,
-                                             int par, int dpar) {
+                                             int par, int dpar, int xpar) {
         const int sub = lane & 15, g = lane >> 4;
         const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
         const float* __restrict__ x = xb + (size_t)(ps.x_off + sub) * BT;
@@ -798,13 +845,14 @@ struct Engine {
         if ((sub & (DIV - 1)) != 0) return;
         const int v0 = (sub / DIV) * NVL;                    // value index = row_in_quad*BT + b
         const int row = ps.dst_row[g] + v0 / BT, b0 = v0 % BT;
-        const bool def = ps.deferred != 0;
-        const int nrow = def ? pl.nrow_d : pl.nrow_c;
-        const uint32_t base = smem_u32(def ? dpart : part);
-        const int bpar = def ? dpar : par;
+        const int dsel = ps.dst;
+        const int nrow = dsel == 0 ? pl.nrow_c : (dsel == 1 ? pl.nrow_d : pl.nrow_x);
+        const uint32_t base = smem_u32(dsel == 0 ? part : (dsel == 1 ? dpart : partx));
+        const int bpar = dsel == 0 ? par : (dsel == 1 ? dpar : xpar);
         const uint32_t off = (uint32_t)((((size_t)bpar * nrow + row) * CS + rank) * BT + b0) * 4u;
         const uint32_t ra = mapa(base + off, (uint32_t)owner);
-        const uint32_t rb = mapa(smem_u32(def ? &bar_dpart[bpar] : &bar_part[bpar]), (uint32_t)owner);
+        const uint32_t rb = mapa(smem_u32(dsel == 0 ? &bar_part[bpar] : (dsel == 1 ? &bar_dpart[bpar] : &bar_partx[bpar])),
+                                 (uint32_t)owner);
         if constexpr (NVL == 1) st_async_f32(ra, acc[0], rb);
         else st_async_f32x2(ra, acc[0], acc[1], rb);
     }
@@ -815,7 +863,7 @@ struct Engine {
         const bool prof = (pp.prof != nullptr) && cw == 0 && lane == 0;
         long long pc[4] = {0, 0, 0, 0}, tc = 0;
 #define WN6_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
-        uint32_t n = 0, nd = 0;
+        uint32_t n = 0, nd = 0, nl = 0;
         const float* blob = nullptr;
         for (int t = 0; t < T && !dead; ++t) {
             if (prof) tc = clock64();
@@ -827,12 +875,23 @@ struct Engine {
                 WN6_TICK(1);
                 const float* xb = xin + (size_t)par * xin_floats;
                 const int begin = pl.pass_begin[kind][cw], cnt = pl.pass_count[kind][cw], crit = pl.pass_crit[kind][cw];
-                const int dpar = nd & 1;
+                const int dpar = nd & 1, xpar = nl & 1;
                 for (int i = 0; i < cnt; ++i) {
-                    run_pass(passes[begin + i], blob, xb, par, dpar);
+                    if (i == crit && nd >= 2) {
+                        // deferred partials reuse the owners' buffer of two deferred stages ago: every owner of the
+                        // cluster must have consumed it (credits sent by the DF warps)
+                        if (!wait_bar<true>(&bar_dfree[dpar], ((nd >> 1) - 1) & 1u, 0x00400000u | (uint32_t)s)) break;
+                    }
+                    run_pass(passes[begin + i], blob, xb, par, dpar, xpar);
                     if (i + 1 == crit) WN6_TICK(2);
                 }
+                if (dead) break;
+                // a warp without deferred passes in this stage still has to consume the credit of its turn
+                if (pl.rows_d[kind] > 0 && cnt == crit && nd >= 2) {
+                    if (!wait_bar<true>(&bar_dfree[dpar], ((nd >> 1) - 1) & 1u, 0x00400000u | (uint32_t)s)) break;
+                }
                 if (pl.rows_d[kind] > 0) ++nd;
+                if (kind == WN6_K_LAYER) ++nl;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_free[par]);
                 if (s < L || s == NS - 1) release_blob(wn6_blob_of_stage(pl, s));
@@ -864,12 +923,14 @@ struct Engine {
     __device__ __forceinline__ uint32_t tx_bytes_c(int kind) const { return (uint32_t)(pl.rows_c[kind] * pl.CS * BT * 4); }
     __device__ __forceinline__ uint32_t tx_bytes_d(int kind) const { return (uint32_t)(pl.rows_d[kind] * pl.CS * BT * 4); }
 
-    __device__ void fin_loop(const bool f0) {
-        const int NS = pl.NS, L = pl.L, T = pp.T, my = pl.my, mx = pl.mx, ms = pl.ms, mo = pl.mo, RA4 = 4 * pl.qA;
-        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
+    __device__ __forceinline__ uint32_t tx_bytes_x() const { return (uint32_t)(pl.rows_x * pl.CS * BT * 4); }
+
+    // F0: gate rows (stages 0..L-1), total skip (stage L), head rows (stages L+1, L+2)
+    __device__ void f0_loop() {
+        const int NS = pl.NS, L = pl.L, T = pp.T, my = pl.my, ms = pl.ms, mo = pl.mo, RA4 = 4 * pl.qA;
         const uint32_t total = (uint32_t)T * (uint32_t)NS;
         const int ND = pl.rows_d[WN6_K_TAIL] > 0 ? L : L - 1;  // deferred stages per step
-        const bool prof = (pp.prof != nullptr) && f0 && lane == 0;
+        const bool prof = (pp.prof != nullptr) && lane == 0;
         long long pc[4] = {0, 0, 0, 0}, tc = 0;
 #define WN6_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
         uint32_t n = 0;
@@ -877,59 +938,42 @@ struct Engine {
             if (prof) tc = clock64();
             for (int s = 0; s < NS; ++s, ++n) {
                 const int par = n & 1, kind = wn6_kind(pl, s);
-                if (!f0 && kind != WN6_K_LAYER) continue;
-                if (f0 && s == 0) {
+                if (s == 0) {
                     if (!wait_bar(bar_pre, (uint32_t)t & 1u, 0x02000000u)) break;     // pre-sums of this step are built
-                }
-                if (!f0 && s == 1) {
-                    // x_0 at the rows this block owns was written by the pollers before they released stage 0
-                    if (!wait_bar(&bar_in[(n - 1) & 1], ((n - 1) >> 1) & 1u, 0x02000001u)) break;
                 }
                 if (!wait_bar(&bar_part[par], (n >> 1) & 1u, 0x04000000u | (uint32_t)s)) break;
                 WN6_TICK(0);
                 __syncwarp();
-                if (f0 && lane == 0 && n + 2 < total) mbar_expect_tx(&bar_part[par], tx_bytes_c(wn6_kind(pl, (s + 2) % NS)));
+                if (lane == 0 && n + 2 < total) mbar_expect_tx(&bar_part[par], tx_bytes_c(wn6_kind(pl, (s + 2) % NS)));
                 const float* P = part + (size_t)par * pl.nrow_c * pl.CS * BT;
                 const uint32_t tag = n + 1u;
                 const long long ex = wn6_ex_off(pl, s, rank);
-                if (f0) {
-                    if (kind == WN6_K_FIRST || kind == WN6_K_LAYER) {
-                        for (int j = lane; j < my * BT; j += 32) {
-                            const int i = j / BT, b = j % BT;
-                            const float a = psum(P, 2 * i, b) + pre[((size_t)s * RA4 + 2 * i) * BT + b];
-                            const float g = psum(P, 2 * i + 1, b) + pre[((size_t)s * RA4 + 2 * i + 1) * BT + b];
-                            publish(ex + (long long)(c * my + i) * BT + b, gate(a, g), tag);
-                        }
-                    } else if (kind == WN6_K_TAIL) {
-                        // skip rows of layers 0..L-2 were accumulated by DF: its deferred stage of layer L-2 must be done
-                        if (L >= 2) wait_count(s_ddone, t * ND + (L - 1), 0x02000002u);
-                        for (int j = lane; j < ms * BT; j += 32) {
-                            const int i = j / BT, b = j % BT;
-                            // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
-                            float tot = psum(P, i, b) + bias[pl.bo_sb + (L - 1) * 4 * pl.qS + i];
-                            if (L >= 2) tot = skipacc[i * BT + b] + tot;
-                            publish(ex + (long long)(c * ms + i) * BT + b, fmaxf(tot * pl.skip_scale, 0.f), tag);
-                        }
-                    } else if (kind == WN6_K_HEAD1) {
-                        for (int j = lane; j < ms * BT; j += 32) {
-                            const int i = j / BT, b = j % BT;
-                            publish(ex + (long long)(c * ms + i) * BT + b, fmaxf(psum(P, i, b) + bias[pl.bo_ha + i], 0.f), tag);
-                        }
-                    } else {
-                        for (int j = lane; j < mo * BT; j += 32) {
-                            const int i = j / BT, b = j % BT;
-                            publish(ex + (long long)(c * mo + i) * BT + b, psum(P, i, b) + bias[pl.bo_hb + i], tag);
-                        }
+                if (kind == WN6_K_FIRST || kind == WN6_K_LAYER) {
+                    for (int j = lane; j < my * BT; j += 32) {
+                        const int i = j / BT, b = j % BT;
+                        const float a = psum(P, 2 * i, b) + pre[((size_t)s * RA4 + 2 * i) * BT + b];
+                        const float g = psum(P, 2 * i + 1, b) + pre[((size_t)s * RA4 + 2 * i + 1) * BT + b];
+                        publish(ex + (long long)(c * my + i) * BT + b, gate(a, g), tag);
+                    }
+                } else if (kind == WN6_K_TAIL) {
+                    // skip rows of layers 0..L-2 were accumulated by DF: its deferred stage of layer L-2 must be done
+                    if (L >= 2) wait_count(s_ddone, t * ND + (L - 1), 0x02000002u);
+                    for (int j = lane; j < ms * BT; j += 32) {
+                        const int i = j / BT, b = j % BT;
+                        // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
+                        float tot = psum(P, i, b) + bias[pl.bo_sb + (L - 1) * 4 * pl.qS + i];
+                        if (L >= 2) tot = skipacc[i * BT + b] + tot;
+                        publish(ex + (long long)(c * ms + i) * BT + b, fmaxf(tot * pl.skip_scale, 0.f), tag);
+                    }
+                } else if (kind == WN6_K_HEAD1) {
+                    for (int j = lane; j < ms * BT; j += 32) {
+                        const int i = j / BT, b = j % BT;
+                        publish(ex + (long long)(c * ms + i) * BT + b, fmaxf(psum(P, i, b) + bias[pl.bo_ha + i], 0.f), tag);
                     }
                 } else {
-                    // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
-                    const float* xprev = (s == 1) ? x0own : xown;
-                    for (int j = lane; j < mx * BT; j += 32) {
+                    for (int j = lane; j < mo * BT; j += 32) {
                         const int i = j / BT, b = j % BT;
-                        const float o = psum(P, RA4 + i, b) + bias[pl.bo_xb + s * 4 * pl.qB + i];
-                        const float xv = (o + xprev[i * BT + b]) * RSQRT2;
-                        publish(ex + (long long)(pl.Ky + c * mx + i) * BT + b, xv, tag);
-                        xown[i * BT + b] = xv;
+                        publish(ex + (long long)(c * mo + i) * BT + b, psum(P, i, b) + bias[pl.bo_hb + i], tag);
                     }
                 }
                 WN6_TICK(1);
@@ -939,6 +983,37 @@ struct Engine {
             for (int i = 0; i < 4; ++i) pp.prof[(size_t)p * 16 + i] = pc[i];
         }
 #undef WN6_TICK
+    }
+
+    // F1: the residual stream of the layer stages, modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
+    __device__ void f1_loop() {
+        const int NS = pl.NS, L = pl.L, T = pp.T, mx = pl.mx;
+        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
+        const uint32_t total = (uint32_t)T * (uint32_t)(L - 1);
+        uint32_t nl = 0;
+        for (int t = 0; t < T && !dead; ++t) {
+            for (int s = 1; s < L; ++s, ++nl) {
+                const int xpar = nl & 1;
+                const uint32_t n = (uint32_t)t * (uint32_t)NS + (uint32_t)s;
+                if (s == 1) {
+                    // x_0 at the rows this block owns was written by the pollers in stage 0 of this step
+                    if (!wait_bar(bar_x0, (uint32_t)t & 1u, 0x02000001u)) break;
+                }
+                if (!wait_bar(&bar_partx[xpar], (nl >> 1) & 1u, 0x04100000u | (uint32_t)s)) break;
+                __syncwarp();
+                if (lane == 0 && nl + 2 < total) mbar_expect_tx(&bar_partx[xpar], tx_bytes_x());
+                const float* P = partx + (size_t)xpar * pl.nrow_x * pl.CS * BT;
+                const long long ex = wn6_ex_off(pl, s, rank);
+                const float* xprev = (s == 1) ? x0own : xown;
+                for (int j = lane; j < mx * BT; j += 32) {
+                    const int i = j / BT, b = j % BT;
+                    const float o = psum(P, i, b) + bias[pl.bo_xb + s * 4 * pl.qB + i];
+                    const float xv = (o + xprev[i * BT + b]) * RSQRT2;
+                    publish(ex + (long long)(pl.Ky + c * mx + i) * BT + b, xv, n + 1u);
+                    xown[i * BT + b] = xv;
+                }
+            }
+        }
     }
 
     // Everything of z_l(t) that does not depend on step t's exchanges: (folded) bias + global conditioning +
@@ -1002,6 +1077,8 @@ struct Engine {
                 }
                 __threadfence_block();
                 __syncwarp();
+                // credit: this owner is done with dpart[dpar]; every block of the cluster may send into it again
+                if (lane < CS) mbar_arrive_remote(mapa(smem_u32(&bar_dfree[dpar]), (uint32_t)lane));
                 ++nd;
                 if (lane == 0) *s_ddone = (int)nd;
             }
@@ -1038,8 +1115,12 @@ wn6_kernel(const __grid_constant__ Wn6Plan pl, const __grid_constant__ Wn6Ptrs p
             mbar_init(&eng.bar_free[i], WN6_NCW);
             mbar_init(&eng.bar_part[i], 1);
             mbar_init(&eng.bar_dpart[i], 1);
+            mbar_init(&eng.bar_partx[i], 1);
+            mbar_init(&eng.bar_dfree[i], (uint32_t)CS);
         }
         mbar_init(eng.bar_pre, 1);
+        mbar_init(eng.bar_x0, 32 * WN6_NPW);
+        mbar_init(eng.bar_ps, 32 * WN6_NPW);
         *eng.s_abort = 0;
         *eng.s_ddone = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1060,6 +1141,7 @@ wn6_kernel(const __grid_constant__ Wn6Plan pl, const __grid_constant__ Wn6Ptrs p
     for (int i = tid; i < 2 * pl.xin_vals * BT; i += WN6_NTHREADS) eng.xin[i] = 0.f;
     for (int i = tid; i < 2 * pl.nrow_c * CS * BT; i += WN6_NTHREADS) eng.part[i] = 0.f;
     for (int i = tid; i < 2 * pl.nrow_d * CS * BT; i += WN6_NTHREADS) eng.dpart[i] = 0.f;
+    for (int i = tid; i < 2 * pl.nrow_x * CS * BT; i += WN6_NTHREADS) eng.partx[i] = 0.f;
     for (int i = tid; i < 4 * pl.qS * BT; i += WN6_NTHREADS) eng.skipacc[i] = 0.f;
     for (int i = tid; i < 8 * pl.qB * BT; i += WN6_NTHREADS) eng.xown[i] = 0.f;
     for (int i = tid; i < pl.O * BT; i += WN6_NTHREADS) eng.hs[i] = 0.f;
@@ -1161,6 +1243,10 @@ wn6_kernel(const __grid_constant__ Wn6Plan pl, const __grid_constant__ Wn6Ptrs p
         // arm the partial-sum barriers of the first two stages / deferred stages
         mbar_expect_tx(&eng.bar_part[0], eng.tx_bytes_c(wn6_kind(pl, 0)));
         mbar_expect_tx(&eng.bar_part[1], eng.tx_bytes_c(wn6_kind(pl, 1)));
+        if (L >= 2) {
+            mbar_expect_tx(&eng.bar_partx[0], eng.tx_bytes_x());
+            mbar_expect_tx(&eng.bar_partx[1], eng.tx_bytes_x());
+        }
         const int ND = pl.rows_d[WN6_K_TAIL] > 0 ? L : L - 1;
         if (ND > 0) {
             mbar_expect_tx(&eng.bar_dpart[0], eng.tx_bytes_d(1 < L ? WN6_K_LAYER : WN6_K_TAIL));
@@ -1172,8 +1258,8 @@ wn6_kernel(const __grid_constant__ Wn6Plan pl, const __grid_constant__ Wn6Ptrs p
 
     if (warp < WN6_NPW) eng.poll_loop();
     else if (warp < WN6_W_F0) eng.comp_loop();
-    else if (warp == WN6_W_F0) eng.fin_loop(true);
-    else if (warp == WN6_W_F1) eng.fin_loop(false);
+    else if (warp == WN6_W_F0) eng.f0_loop();
+    else if (warp == WN6_W_F1) eng.f1_loop();
     else if (warp == WN6_W_DF) eng.dfin_loop();
     else if (warp == WN6_W_TMA) eng.tma_loop();
     else if (pl.C > 0) eng.cond_loop();

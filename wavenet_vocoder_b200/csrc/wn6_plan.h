@@ -66,7 +66,8 @@ struct Wn6Pass {
     int16_t x_off;        // first k of the tile in the stage input slice
     int16_t dst_row[2];   // per lane group: first row slot in the owner's partial buffer
     int8_t owner[2];      // per lane group: owner rank inside the cluster, -1 = idle quad
-    int8_t deferred;      // 0: critical partial buffer, 1: deferred partial buffer
+    int8_t dst;           // partial buffer of the owner: 0 = F0 (gate / skip / head rows), 1 = DF (deferred rows),
+                          // 2 = F1 (residual rows)
     int8_t job;           // WN6_J_*  (packer / tests only)
     int16_t quad[2];      // per lane group: quad index inside the job (packer / tests only)
 };
@@ -88,10 +89,12 @@ struct Wn6Plan {
     int NS;                     // stages per step = L+3
     int rs_yx, rs_sk, rs_h2;    // per-rank stride of a slice
     long long ex_yx, ex_sk, ex_h1, ex_h2, ex_pairs;
-    // ---- partial buffers of an owner (rows x CS x BT floats, double buffered by stage parity)
-    int nrow_c, nrow_d;
-    int rows_c[WN6_NKIND];      // critical rows sent per stage kind (tx bytes = rows*CS*BT*4)
-    int rows_d[WN6_NKIND];      // deferred rows sent per stage kind
+    // ---- partial buffers of an owner (rows x CS x BT floats, double buffered): one per finaliser warp, each
+    // with its own mbarrier pair, so that every barrier is armed and waited on by exactly one warp
+    int nrow_c, nrow_d, nrow_x;
+    int rows_c[WN6_NKIND];      // rows sent to F0 per stage kind (tx bytes = rows*CS*BT*4)
+    int rows_d[WN6_NKIND];      // rows sent to DF per stage kind
+    int rows_x;                 // rows sent to F1 in a layer stage
     // ---- pass lists: pass_begin[kind][warp] .. +pass_count, the first pass_crit of them critical
     int npass;
     int pass_begin[WN6_NKIND][WN6_NCW], pass_count[WN6_NKIND][WN6_NCW], pass_crit[WN6_NKIND][WN6_NCW];
@@ -107,7 +110,7 @@ struct Wn6Plan {
     int ring_in_smem;
     long long ring_pos_total;
     // ---- shared memory map (byte offsets)
-    int sm_bar, sm_misc, sm_pass, sm_ringtab, sm_xin, sm_part, sm_dpart, sm_sb, sm_pre, sm_cond, sm_bias,
+    int sm_bar, sm_misc, sm_pass, sm_ringtab, sm_xin, sm_part, sm_dpart, sm_partx, sm_sb, sm_pre, sm_cond, sm_bias,
         sm_skipacc, sm_xown, sm_hs, sm_noise, sm_in, sm_x0w, sm_ring, sm_slots, smem_bytes;
 };
 
