@@ -102,6 +102,9 @@ typedef struct wn_generate_args {
     int32_t B;                 /* utterances (rows of the batch); any B >= 1               */
     int32_t T;                 /* samples to generate per utterance                         */
     const float* c;            /* (B,T,C) local conditioning at SAMPLE rate (after upsample, wavenet.py:272-278) */
+    const float* c_frames;     /* or: (B,C,n_frames) conditioning FRAMES, upsampled on the device by the network given to
+                                  wn_load_upsampler (upsample.py:29-85, wavenet.py:274-276); exclusive with `c`          */
+    int32_t n_frames;
     const float* g;            /* (B,gin) global conditioning vector (after embedding, wavenet.py:263-268)       */
     const float* initial;      /* scalar input: (B) ; one-hot input: NULL (default index) -- wavenet.py:281-292   */
     int32_t initial_index;     /* one-hot input: start class (reference default 127, wavenet.py:286); <0 = 127     */
@@ -153,6 +156,34 @@ int32_t wn_destroy(void* handle);
 
 /* Upload weights (HOST fp32, folded).  Packs them per thread block and copies to the device. */
 int32_t wn_load_weights(void* handle, const wn_weights* w);
+
+/* Local-conditioning upsampler (reference upsample.py): optional conv_in over frames, then per scale a
+ * nearest-neighbour stretch and a 1 x (2s+1) smoothing filter shared by all channels.  HOST pointers, weight norm
+ * already folded.  Only the common configuration is supported natively (freq_axis_kernel_size 1, no activation,
+ * nearest mode, every scale >= 2); callers keep other variants on their own side and pass `c`. */
+typedef struct wn_upsampler {
+    int32_t channels;          /* C (== cin_channels)                                                      */
+    int32_t n_scales;          /* <= 8                                                                     */
+    const int32_t* scales;     /* [n_scales] upsample_scales                                               */
+    const float* filters;      /* concatenated smoothing filters, 2*s_j+1 taps each (Conv2d weight (1,1,1,2s+1)) */
+    const float* conv_in_w;    /* (C,C,conv_in_ks) ConvInUpsampleNetwork.conv_in.weight, or NULL           */
+    int32_t conv_in_ks;        /* 2*cin_pad+1, or 0                                                        */
+    int32_t indent;            /* samples trimmed at both ends: cin_pad*prod(scales) for UpsampleNetwork, else 0 */
+    int32_t reserved[5];
+} wn_upsampler;
+int32_t wn_load_upsampler(void* handle, const wn_upsampler* u);
+/* Run only the upsampler: c_frames (B,C,n_frames) -> out (B,T,C), DEVICE pointers, T = upsampled length. */
+int32_t wn_upsample(void* handle, const float* c_frames, int32_t B, int32_t n_frames, int32_t T, float* out,
+                    void* stream);
+
+/* Decode synthesis output to audio (synthesis.py:66-84 + evaluate.py:43-48,247-251): inverse mu-law for
+ * input_type 1 ("mulaw", y_scalar) / 2 ("mulaw-quantize", y_index), nothing for 0 ("raw"); then
+ * inv_preemphasis (preemphasis_coef != 0), division by global_gain_scale (> 0), and -- for out_pcm16 -- trimming to
+ * lengths[b] (zeros beyond), clip to [-1,1] and (x*32767) truncated to int16.  DEVICE pointers; (B,T) each. */
+enum { WN_DECODE_RAW = 0, WN_DECODE_MULAW = 1, WN_DECODE_MULAW_QUANTIZE = 2 };
+int32_t wn_decode(const float* y_scalar, const int32_t* y_index, int32_t B, int32_t T, const int32_t* lengths,
+                  int32_t input_type, int32_t quantize_channels, float preemphasis_coef, float global_gain_scale,
+                  float* out_float, int16_t* out_pcm16, void* stream);
 
 /* Run one synthesis call; returns after the launch is enqueued on args->stream.
  * wn_sync() waits for it and reports a device-side fault/timeout as WN_ERR_DEVICE. */

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libwn.so")
 SOURCES = [os.path.join(HERE, "csrc", "wn_host.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("wn_plan.h", "wn_kernel.cuh", "wn6_plan.h", "wn6_kernel.cuh",
-                                                     "wn6_host.cuh")] + [os.path.join(ROOT, "include", "wn.h")]
+                                                     "wn6_host.cuh", "wn_aux.cuh")] + [os.path.join(ROOT, "include", "wn.h")]
 
 WN_ABI_VERSION = 2
 WN_INPUT_SCALAR, WN_INPUT_ONEHOT = 0, 1
@@ -48,7 +48,7 @@ class wn_weights(C.Structure):
 class wn_generate_args(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("T", C.c_int32),
-        ("c", C.c_void_p), ("g", C.c_void_p), ("initial", C.c_void_p),
+        ("c", C.c_void_p), ("c_frames", C.c_void_p), ("n_frames", C.c_int32), ("g", C.c_void_p), ("initial", C.c_void_p),
         ("initial_index", C.c_int32), ("initial_rows", C.c_void_p), ("initial_dense", C.c_void_p),
         ("T_test", C.c_int32),
         ("test_scalar", C.c_void_p), ("test_index", C.c_void_p), ("test_dense", C.c_void_p),
@@ -59,6 +59,14 @@ class wn_generate_args(C.Structure):
         ("params_out", C.c_void_p), ("stream", C.c_void_p),
         ("reserved", C.c_int32 * 8),
     ]
+
+
+class wn_upsampler(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("n_scales", C.c_int32), ("scales", _i32p), ("filters", _f32p),
+                ("conv_in_w", _f32p), ("conv_in_ks", C.c_int32), ("indent", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+WN_DECODE_RAW, WN_DECODE_MULAW, WN_DECODE_MULAW_QUANTIZE = 0, 1, 2
 
 
 class wn_plan_info(C.Structure):
@@ -122,7 +130,7 @@ def plan_passes(cfg, batch=1, num_sms=148, smem=232448):
 # every symbol include/wn.h declares (tests check the .so exports all of them)
 EXPORTS = ["wn_abi_version", "wn_last_error", "wn_create", "wn_destroy", "wn_load_weights",
            "wn_generate", "wn_sync", "wn_generate_host", "wn_get_plan", "wn_plan_only",
-           "wn_pack_cta", "wn_plan_passes", "wn_sample_mol", "wn_sample_gauss"]
+           "wn_pack_cta", "wn_plan_passes", "wn_load_upsampler", "wn_upsample", "wn_decode", "wn_sample_mol", "wn_sample_gauss"]
 
 
 def nvcc_command(out=LIB_PATH):
@@ -181,6 +189,10 @@ def lib():
                               C.c_int32, _f32p, C.c_int64]
     L.wn_plan_passes.argtypes = [C.POINTER(wn_config), C.c_int32, C.c_int32, C.c_int64, _i32p, C.c_int32,
                                  C.c_void_p, C.c_int32]
+    L.wn_load_upsampler.argtypes = [C.c_void_p, C.POINTER(wn_upsampler)]
+    L.wn_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.wn_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                            C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     L.wn_sample_mol.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]
     L.wn_sample_gauss.argtypes = L.wn_sample_mol.argtypes

@@ -16,6 +16,7 @@
 #include "wn_kernel.cuh"
 #include "wn6_plan.h"
 #include "wn6_kernel.cuh"
+#include "wn_aux.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -439,6 +440,14 @@ struct WnHandle {
     int max_clusters = 0;
     bool attr6_set[4] = {};
     bool coop_with_clusters = true;
+    // local-conditioning upsampler (wn_load_upsampler)
+    bool have_ups = false;
+    wnaux::UpsampleDesc ups;
+    int ups_C = 0, ups_ks = 0, ups_total = 1;
+    float *d_ups_filters = nullptr, *d_ups_convw = nullptr;
+    float* d_cup = nullptr;  size_t cup_bytes = 0;     // (B,T,C) upsampled conditioning
+    float* d_hfr = nullptr;  size_t hfr_bytes = 0;     // (B,F',C) frames after conv_in
+    bool ups_attr = false;
     int num_sms = 0;
     long long smem_cap = 0;
     bool have_weights = false;
@@ -640,6 +649,33 @@ static void fill_info6(const wn_config& c, const Wn6Plan& pl, wn_plan_info* out)
     int64_t streamed = 0;
     for (int i = pl.nres; i < pl.nblobs; ++i) streamed += wn6_blob_floats(pl, i) * 4LL;
     out->streamed_bytes_per_step = streamed * pl.P;
+}
+
+static int32_t run_upsampler(WnHandle* h, const float* c_frames, int B, int F, int T, cudaStream_t st) {
+    const int C = h->ups_C;
+    const int Fo = F - (h->ups_ks > 0 ? h->ups_ks - 1 : 0);
+    int32_t rc = ensure(&h->d_hfr, &h->hfr_bytes, (size_t)B * Fo * C * sizeof(float));
+    if (rc) return rc;
+    rc = ensure(&h->d_cup, &h->cup_bytes, (size_t)B * T * C * sizeof(float));
+    if (rc) return rc;
+    const long long n = (long long)B * Fo * C;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 4096);
+    if (h->ups_ks > 0)
+        wnaux::conv_in_kernel<<<blocks, 256, 0, st>>>(c_frames, h->d_ups_convw, h->d_hfr, B, C, F, h->ups_ks);
+    else
+        wnaux::frames_to_fc_kernel<<<blocks, 256, 0, st>>>(c_frames, h->d_hfr, B, C, F);
+    CUDA_TRY(cudaGetLastError());
+    constexpr int TS = 256;
+    const size_t smem = 2ull * (TS / 2 + 8) * C * sizeof(float);
+    if (!h->ups_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(wnaux::upsample_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->ups_attr = true;
+    }
+    wnaux::upsample_kernel<TS><<<dim3((T + TS - 1) / TS, B), 256, smem, st>>>(h->d_hfr, h->d_ups_filters, h->ups, C, Fo, T,
+                                                                            h->d_cup);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    return WN_OK;
 }
 
 static const void* kernel6_for(int BT) {
@@ -946,6 +982,7 @@ int32_t wn_destroy(void* handle) {
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(h->d_bpack); cudaFree(h->d_passes);
+    cudaFree(h->d_ups_filters); cudaFree(h->d_ups_convw); cudaFree(h->d_cup); cudaFree(h->d_hfr);
     cudaFree(h->d_wpack); cudaFree(h->d_cwpack); cudaFree(h->d_wg); cudaFree(h->d_first_w); cudaFree(h->d_first_b);
     cudaFree(h->d_ringtab); cudaFree(h->d_err); cudaFree(h->d_xbuf); cudaFree(h->d_ring); cudaFree(h->d_gbias);
     cudaFree(h->d_scratch);
@@ -1037,8 +1074,15 @@ static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
     if (!a) return fail(WN_ERR_INVALID, "null args");
     if (a->B < 1 || a->T < 1) return fail(WN_ERR_INVALID, "B and T must be >= 1");
     if ((long long)a->T * (c.layers + 3LL) >= 0xFFFFFFF0LL) return fail(WN_ERR_INVALID, "T too large for 32-bit tags");
-    if (c.cin_channels > 0 && !a->c) return fail(WN_ERR_INVALID, "c is required (cin_channels > 0), cf. train.py:82-87");
-    if (c.cin_channels == 0 && a->c) return fail(WN_ERR_INVALID, "c given but the model has no local conditioning");
+    if (a->c && a->c_frames) return fail(WN_ERR_INVALID, "give either c (sample rate) or c_frames, not both");
+    if (c.cin_channels > 0 && !a->c && !a->c_frames) return fail(WN_ERR_INVALID, "c is required (cin_channels > 0), cf. train.py:82-87");
+    if (c.cin_channels == 0 && (a->c || a->c_frames)) return fail(WN_ERR_INVALID, "c given but the model has no local conditioning");
+    if (a->c_frames) {
+        if (!h->have_ups) return fail(WN_ERR_STATE, "c_frames given but no upsampler was loaded (wn_load_upsampler)");
+        const long long Fo = (long long)a->n_frames - (h->ups_ks > 0 ? h->ups_ks - 1 : 0);
+        if (Fo < 1 || Fo * h->ups_total - 2LL * h->ups.indent != (long long)a->T)
+            return fail(WN_ERR_INVALID, "upsampled conditioning length != T (wavenet.py:276)");
+    }
     if (c.gin_channels == 0 && a->g) return fail(WN_ERR_INVALID, "g given but the model has no global conditioning");
     if (a->T_test < 0 || a->T_test > a->T) return fail(WN_ERR_INVALID, "T_test must be in [0,T] (wavenet.py:258)");
     if (c.input_kind == WN_INPUT_SCALAR) {
@@ -1077,6 +1121,15 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
     if (rc) return rc;
     DeviceGuard guard(h->cfg.device);
     cudaStream_t st = (cudaStream_t)a->stream;
+    wn_generate_args up_args;
+    if (a->c_frames) {
+        rc = run_upsampler(h, a->c_frames, a->B, a->n_frames, a->T, st);
+        if (rc) return rc;
+        up_args = *a;
+        up_args.c = h->d_cup;
+        up_args.c_frames = nullptr;
+        a = &up_args;
+    }
     // batch tiles: up to 8 utterances share one launch (one pass over the weights per step for all of them)
     const int tile = max_tile(h->engine);
     for (int b0 = 0; b0 < a->B; b0 += tile) {
@@ -1170,6 +1223,7 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
         return v.back().off;
     };
     const size_t o_c = add(in, a->c, nullptr, B * T * (size_t)c.cin_channels * 4);
+    const size_t o_cf = add(in, a->c_frames, nullptr, B * (size_t)c.cin_channels * (size_t)std::max(a->n_frames, 0) * 4);
     const size_t o_g = add(in, a->g, nullptr, B * (size_t)c.gin_channels * 4);
     const size_t o_init = add(in, a->initial, nullptr, B * 4);
     const size_t o_irow = add(in, a->initial_rows, nullptr, B * 4);
@@ -1193,6 +1247,7 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
     wn_generate_args d = *a;
     auto dp = [&](size_t off) -> char* { return off == (size_t)-1 ? nullptr : base + off; };
     d.c = (const float*)dp(o_c);
+    d.c_frames = (const float*)dp(o_cf);
     d.g = (const float*)dp(o_g);
     d.initial = (const float*)dp(o_init);
     d.initial_rows = (const int32_t*)dp(o_irow);
@@ -1212,6 +1267,79 @@ int32_t wn_generate_host(void* handle, const wn_generate_args* a) {
     if (rc) return rc;
     for (const Item& it : out) CUDA_TRY(cudaMemcpyAsync(it.dst_host, base + it.off, it.bytes, cudaMemcpyDeviceToHost, st));
     return wn_sync(handle);
+}
+
+int32_t wn_load_upsampler(void* handle, const wn_upsampler* u) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h) return fail(WN_ERR_INVALID, "null handle");
+    DeviceGuard guard(h->cfg.device);
+    h->have_ups = false;
+    if (!u) return WN_OK;
+    if (u->channels != h->cfg.cin_channels || u->channels < 1) return fail(WN_ERR_INVALID, "upsampler channels != cin_channels");
+    if (u->n_scales < 1 || u->n_scales > WNAUX_MAX_SCALES || !u->scales || !u->filters)
+        return fail(WN_ERR_INVALID, "upsampler needs 1..8 scales and their filters");
+    if ((u->conv_in_w != nullptr) != (u->conv_in_ks > 0) || u->indent < 0) return fail(WN_ERR_INVALID, "bad conv_in / indent");
+    memset(&h->ups, 0, sizeof(h->ups));
+    h->ups.n_scales = u->n_scales;
+    h->ups.indent = u->indent;
+    int off = 0;
+    long long total = 1;
+    for (int j = 0; j < u->n_scales; ++j) {
+        const int s = u->scales[j];
+        if (s < 2 || s > 4096) return fail(WN_ERR_INVALID, "every upsample scale must be in [2,4096]");
+        h->ups.scales[j] = s;
+        h->ups.foff[j] = off;
+        h->ups.rscale[j] = (float)(1.0 / (double)s);
+        off += 2 * s + 1;
+        total *= s;
+        if (total > (1 << 24)) return fail(WN_ERR_INVALID, "total upsample scale too large");
+    }
+    h->ups_total = (int)total;
+    h->ups_C = u->channels;
+    h->ups_ks = u->conv_in_ks;
+    if (h->d_ups_filters) cudaFree(h->d_ups_filters);
+    h->d_ups_filters = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_ups_filters, (size_t)off * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(h->d_ups_filters, u->filters, (size_t)off * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->d_ups_convw) cudaFree(h->d_ups_convw);
+    h->d_ups_convw = nullptr;
+    if (u->conv_in_ks > 0) {
+        const size_t nw = (size_t)u->channels * u->channels * u->conv_in_ks;
+        CUDA_TRY(cudaMalloc((void**)&h->d_ups_convw, nw * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(h->d_ups_convw, u->conv_in_w, nw * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    h->have_ups = true;
+    return WN_OK;
+}
+
+int32_t wn_upsample(void* handle, const float* c_frames, int32_t B, int32_t n_frames, int32_t T, float* out, void* stream) {
+    WnHandle* h = (WnHandle*)handle;
+    if (!h || !c_frames || !out) return fail(WN_ERR_INVALID, "null argument");
+    if (!h->have_ups) return fail(WN_ERR_STATE, "no upsampler was loaded (wn_load_upsampler)");
+    const long long Fo = (long long)n_frames - (h->ups_ks > 0 ? h->ups_ks - 1 : 0);
+    if (B < 1 || Fo < 1 || Fo * h->ups_total - 2LL * h->ups.indent != (long long)T)
+        return fail(WN_ERR_INVALID, "upsampled conditioning length != T (wavenet.py:276)");
+    DeviceGuard guard(h->cfg.device);
+    int32_t rc = run_upsampler(h, c_frames, B, n_frames, T, (cudaStream_t)stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_cup, (size_t)B * T * h->ups_C * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return WN_OK;
+}
+
+int32_t wn_decode(const float* y_scalar, const int32_t* y_index, int32_t B, int32_t T, const int32_t* lengths,
+                  int32_t input_type, int32_t quantize_channels, float preemphasis_coef, float global_gain_scale,
+                  float* out_float, int16_t* out_pcm16, void* stream) {
+    if (B < 1 || T < 1) return fail(WN_ERR_INVALID, "B and T must be >= 1");
+    if (!out_float && !out_pcm16) return fail(WN_ERR_INVALID, "no output buffer");
+    if (input_type == WN_DECODE_MULAW_QUANTIZE ? !y_index : !y_scalar) return fail(WN_ERR_INVALID, "missing input for this input_type");
+    if (input_type < 0 || input_type > 2) return fail(WN_ERR_INVALID, "bad input_type");
+    if (input_type != WN_DECODE_RAW && quantize_channels < 2) return fail(WN_ERR_INVALID, "quantize_channels must be >= 2");
+    wnaux::decode_kernel<1024><<<B, 256, 0, (cudaStream_t)stream>>>(y_scalar, y_index, T, lengths, input_type,
+                                                                    (float)(quantize_channels - 1), preemphasis_coef,
+                                                                    global_gain_scale, out_float, (short*)out_pcm16);
+    CUDA_TRY(cudaGetLastError());
+    return WN_OK;
 }
 
 int32_t wn_sample_mol(const float* y_bot, int32_t B, int32_t O, int32_t T, const float* u1_tbk, const float* u2_tb,

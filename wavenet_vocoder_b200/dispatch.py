@@ -7,8 +7,9 @@ decode and write 16-bit wav files -- re-organised for the engine:
   device (evaluate.py:50-58, :162-204).  Here utterances are sharded over ranks by total length
   (``parallel.shard_utterances``) and, inside a rank, sorted by length and grouped into launches of at
   most ``tile`` utterances, so the padding inside a launch is small;
-* decode follows synthesis.py:66-84 / evaluate.py:215-251: class ids -> inverse mu-law, optional inverse
-  pre-emphasis, gain, trim to the utterance's own length, clip, int16.
+* decode follows synthesis.py:66-84 / evaluate.py:215-251 -- class ids -> inverse mu-law, optional inverse
+  pre-emphasis, gain, trim to the utterance's own length, clip, int16 -- as one device kernel of libwn
+  (``decode_device``; csrc/wn_aux.cuh) writing int16 directly.
 
 File formats are the reference's: ``<name>-feats.npy`` = (frames, num_mels) float32 written by
 ``datasets/wavallin.py`` (np.save, :104-107); output ``<name>_gen.wav`` (evaluate.py:229-231).
@@ -26,31 +27,44 @@ import torch.nn.functional as F
 from .parallel import shard_utterances, tile_batches
 
 
-def inv_mulaw(y: np.ndarray, mu: int = 255) -> np.ndarray:
-    """[-1,1] mu-law companded -> linear (what nnmnkwii's ``inv_mulaw`` does for synthesis.py:71-74)."""
-    y = np.asarray(y, dtype=np.float32)
-    return np.sign(y) * (1.0 / mu) * ((1.0 + mu) ** np.abs(y) - 1.0)
+INPUT_TYPES = {"raw": 0, "mulaw": 1, "mulaw-quantize": 2}
 
 
-def inv_mulaw_quantize(idx: np.ndarray, mu: int = 255) -> np.ndarray:
-    """class ids in [0, mu] -> linear waveform in [-1, 1] (synthesis.py:66-70)."""
-    y = 2.0 * np.asarray(idx, dtype=np.float32) / mu - 1.0
-    return inv_mulaw(y, mu)
-
-
-def inv_preemphasis(x: np.ndarray, coef: float = 0.85) -> np.ndarray:
-    """audio.py:57-58: y[n] = x[n] + coef * y[n-1]."""
-    from scipy import signal
-    return signal.lfilter([1.0], [1.0, -coef], x).astype(np.float32)
-
-
-def to_int16(x: np.ndarray) -> np.ndarray:
-    """evaluate.py:43-48."""
-    if x.dtype == np.int16:
-        return x
-    x = np.asarray(x, dtype=np.float32)
-    assert x.min() >= -1 and x.max() <= 1.0
-    return (x * 32767).astype(np.int16)
+def decode_device(y_hat: torch.Tensor, lengths: Optional[Sequence[int]] = None, input_type: str = "raw",
+                  quantize_channels: int = 65536, postprocess: Optional[str] = None,
+                  global_gain_scale: float = 0.0, preemphasis_coef: float = 0.85, want_float: bool = False):
+    """Model output (B,C,T) on the GPU -> int16 waveforms (B,T) on the GPU (and, optionally, the float waveforms
+    ``batch_wavegen`` returns), in ONE kernel of libwn (csrc/wn_aux.cuh): inverse mu-law for "mulaw" /
+    "mulaw-quantize" (synthesis.py:66-74), inv_preemphasis when ``postprocess == "inv_preemphasis"``
+    (synthesis.py:76-78, audio.py:57-58), division by ``global_gain_scale`` (synthesis.py:80-82), trim to
+    ``lengths`` (zeros beyond), clip and int16 (evaluate.py:215,247,43-48).  No CPU path: raises off the GPU."""
+    import ctypes as C
+    from . import _native as N
+    if y_hat.device.type != "cuda":
+        raise RuntimeError("decode_device runs on a CUDA tensor only (no CPU fallback)")
+    if postprocess not in (None, "", "none", "inv_preemphasis"):
+        raise ValueError("unsupported postprocess %r" % (postprocess,))
+    B = y_hat.size(0)
+    kind = INPUT_TYPES[input_type]
+    y_s = y_i = None
+    if kind == 2:
+        y_i = y_hat.max(1)[1].view(B, -1).to(torch.int32).contiguous()          # synthesis.py:68
+        T = y_i.size(1)
+    else:
+        y_s = y_hat.reshape(B, -1).float().contiguous()
+        T = y_s.size(1)
+    dev = y_hat.device
+    len_t = None if lengths is None else torch.tensor([int(v) for v in lengths], dtype=torch.int32, device=dev)
+    pcm = torch.empty(B, T, dtype=torch.int16, device=dev)
+    flt = torch.empty(B, T, dtype=torch.float32, device=dev) if want_float else None
+    coef = float(preemphasis_coef) if postprocess == "inv_preemphasis" else 0.0
+    with torch.cuda.device(dev):
+        N.check(N.lib().wn_decode(None if y_s is None else y_s.data_ptr(), None if y_i is None else y_i.data_ptr(), B, T,
+                                  None if len_t is None else len_t.data_ptr(), kind, int(quantize_channels),
+                                  C.c_float(coef), C.c_float(float(global_gain_scale)),
+                                  None if flt is None else flt.data_ptr(), pcm.data_ptr(),
+                                  torch.cuda.current_stream(dev).cuda_stream))
+    return (pcm, flt) if want_float else pcm
 
 
 def list_feature_files(data_dir: str) -> List[str]:
@@ -74,32 +88,16 @@ def collate(feats: Sequence[np.ndarray], cin_pad: int) -> torch.Tensor:
     return ct
 
 
-def decode(y_hat: torch.Tensor, input_type: str = "raw", quantize_channels: int = 65536,
-           postprocess: Optional[str] = None, global_gain_scale: float = 0.0) -> np.ndarray:
-    """Model output (B,C,T) -> float waveforms (B,T) as synthesis.py:66-84 does."""
-    B = y_hat.size(0)
-    if input_type == "mulaw-quantize":
-        out = inv_mulaw_quantize(y_hat.max(1)[1].view(B, -1).cpu().numpy(), quantize_channels - 1)
-    elif input_type == "mulaw":
-        out = inv_mulaw(y_hat.view(B, -1).cpu().numpy(), quantize_channels - 1)
-    else:
-        out = y_hat.view(B, -1).cpu().numpy().astype(np.float32)
-    if postprocess == "inv_preemphasis":
-        out = np.stack([inv_preemphasis(o) for o in out])
-    if global_gain_scale > 0:
-        out = out / global_gain_scale
-    return out
-
-
 def synthesize_directory(model, data_dir: str, dst_dir: str, *, hop_size: int, cin_pad: int = 0,
                          sample_rate: int = 22050, tile: int = 4, rank: int = 0, world: int = 1,
                          input_type: str = "raw", quantize_channels: int = 65536,
                          postprocess: Optional[str] = None, global_gain_scale: float = 0.0,
                          synth: Optional[Callable[[torch.Tensor, int], torch.Tensor]] = None,
-                         write: bool = True) -> Dict[str, np.ndarray]:
+                         decode: Optional[Callable] = None, write: bool = True) -> Dict[str, np.ndarray]:
     """Synthesise this rank's share of ``data_dir`` and write ``<name>_gen.wav`` into ``dst_dir``.
-    ``synth(c, T)`` defaults to ``model.incremental_forward(c=c, T=T)`` (c: (B, D, frames + 2*cin_pad)).
-    Returns {name: int16 waveform} for the utterances handled by this rank."""
+    ``synth(c, T)`` defaults to ``model.incremental_forward(c=c, T=T)`` (c: (B, D, frames + 2*cin_pad));
+    ``decode(y_hat, lengths) -> (B,T) int16`` defaults to the device kernel (``decode_device``).  Both hooks exist
+    for the host-logic tests, which run without a GPU.  Returns {name: int16 waveform} for this rank's utterances."""
     from scipy.io import wavfile
     files = list_feature_files(data_dir)
     feats = [np.load(f).astype(np.float32) for f in files]
@@ -109,17 +107,20 @@ def synthesize_directory(model, data_dir: str, dst_dir: str, *, hop_size: int, c
         def synth(c, T):
             with torch.no_grad():
                 return model.incremental_forward(c=c, T=T)
+    if decode is None:
+        def decode(y_hat, lens):
+            return decode_device(y_hat, lens, input_type, quantize_channels, postprocess, global_gain_scale)
     if write:
         os.makedirs(dst_dir, exist_ok=True)
     results: Dict[str, np.ndarray] = {}
     for launch in tile_batches(mine, lengths, tile):
         c = collate([feats[i] for i in launch], cin_pad)
         T = (c.shape[-1] - 2 * cin_pad) * hop_size
-        waves = decode(synth(c, T), input_type, quantize_channels, postprocess, global_gain_scale)
+        pcm_all = decode(synth(c, T), [lengths[i] for i in launch])
+        pcm_all = pcm_all.cpu().numpy() if isinstance(pcm_all, torch.Tensor) else np.asarray(pcm_all)
         for row, i in enumerate(launch):
-            gen = np.clip(waves[row][:lengths[i]], -1.0, 1.0)          # trim the batch padding (evaluate.py:215,247)
+            pcm = pcm_all[row][:lengths[i]].astype(np.int16)            # trim the batch padding (evaluate.py:215)
             name = os.path.splitext(os.path.basename(files[i]))[0].replace("-feats", "")
-            pcm = to_int16(gen.astype(np.float32))
             results[name] = pcm
             if write:
                 wavfile.write(os.path.join(dst_dir, "%s_gen.wav" % name), sample_rate, pcm)

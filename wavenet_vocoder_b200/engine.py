@@ -145,6 +145,78 @@ class SynthesisEngine:
         N.check(N.lib().wn_load_weights(self._h, C.byref(w)))
         del keep
 
+    def load_upsampler(self, net) -> bool:
+        """Hand the local-conditioning upsampler (upsample.py:29-85 there) to libwn so that ``generate`` can take
+        raw conditioning frames.  Returns False (and unloads) for variants the native path does not cover
+        (freq_axis_kernel_size != 1, an activation, a non-nearest mode, a scale < 2): the caller then keeps
+        them on the PyTorch side and passes sample-rate ``c``."""
+        from . import upsample as U
+        self.ups_frames_lost = 0
+        self.ups_total = 1
+        N.check(N.lib().wn_load_upsampler(self._h, None))
+        if net is None or self.cin <= 0:
+            return False
+        conv_in = None
+        up = net
+        if isinstance(net, U.ConvInUpsampleNetwork):
+            conv_in, up = net.conv_in, net.upsample
+        if not isinstance(up, U.UpsampleNetwork):
+            return False
+        scales, filters = [], []
+        layers = list(up.up_layers)
+        if len(layers) % 2 != 0:
+            return False                                   # an activation follows every conv
+        for st, conv in zip(layers[0::2], layers[1::2]):
+            if not isinstance(st, U.Stretch2d) or st.mode != "nearest" or st.y_scale != 1:
+                return False
+            sd = {k: v for k, v in conv.state_dict().items()}
+            if "weight" in sd:
+                w = sd["weight"].detach().float().cpu()
+            else:
+                w = torch._weight_norm(sd["weight_v"].detach().float().cpu(), sd["weight_g"].detach().float().cpu(), 0)
+            s = int(st.x_scale)
+            if w.shape != (1, 1, 1, 2 * s + 1) or s < 2:
+                return False
+            scales.append(s)
+            filters.append(w.reshape(-1))
+        if not scales or len(scales) > 8:
+            return False
+        u = N.wn_upsampler()
+        u.channels = self.cin
+        u.n_scales = len(scales)
+        sc = (C.c_int32 * len(scales))(*scales)
+        fl = torch.cat(filters).contiguous()
+        u.scales = sc
+        u.filters = C.cast(fl.data_ptr(), C.POINTER(C.c_float))
+        cw = None
+        if conv_in is not None:
+            cw = conv_in.weight.detach().float().cpu().contiguous()
+            if cw.shape[0] != self.cin or cw.shape[1] != self.cin or conv_in.bias is not None:
+                return False
+            u.conv_in_w = C.cast(cw.data_ptr(), C.POINTER(C.c_float))
+            u.conv_in_ks = int(cw.shape[2])
+        u.indent = int(up.indent)
+        N.check(N.lib().wn_load_upsampler(self._h, C.byref(u)))
+        self.ups_total = 1
+        for s in scales:
+            self.ups_total *= s
+        self.ups_frames_lost = (int(cw.shape[2]) - 1 if cw is not None else 0)
+        self.ups_indent = int(up.indent)
+        return True
+
+    def upsample(self, c_frames: torch.Tensor, T: int) -> torch.Tensor:
+        """(B,C,frames) -> (B,T,C): only the upsampler of libwn (tests / tools)."""
+        B = c_frames.size(0)
+        cf = c_frames.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty(B, T, self.cin, device=self.device, dtype=torch.float32)
+        N.check(N.lib().wn_upsample(self._h, cf.data_ptr(), B, int(cf.size(-1)), int(T), out.data_ptr(),
+                                    torch.cuda.current_stream(self.device).cuda_stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def upsampled_length(self, n_frames: int) -> int:
+        return (n_frames - self.ups_frames_lost) * self.ups_total - 2 * self.ups_indent
+
     def plan(self, batch=1) -> dict:
         info = N.wn_plan_info()
         N.check(N.lib().wn_get_plan(self._h, int(batch), C.byref(info)))
@@ -152,7 +224,7 @@ class SynthesisEngine:
 
     # ------------------------------------------------------------------ one synthesis call
     def generate(self, *, B: int, T: int, c: Optional[torch.Tensor] = None,
-                 g: Optional[torch.Tensor] = None, initial: Optional[torch.Tensor] = None,
+                 c_frames: Optional[torch.Tensor] = None, g: Optional[torch.Tensor] = None, initial: Optional[torch.Tensor] = None,
                  initial_index: int = -1, initial_rows: Optional[torch.Tensor] = None,
                  initial_dense: Optional[torch.Tensor] = None, test_scalar: Optional[torch.Tensor] = None,
                  test_index: Optional[torch.Tensor] = None,
@@ -177,6 +249,9 @@ class SynthesisEngine:
             return t.data_ptr()
 
         a.c = dptr(c, shape=(B, T, self.cin) if c is not None else None)
+        if c_frames is not None:
+            a.c_frames = dptr(c_frames, shape=(B, self.cin, c_frames.size(-1)))
+            a.n_frames = int(c_frames.size(-1))
         a.g = dptr(g, shape=(B, self.gin) if g is not None else None)
         a.initial = dptr(initial, shape=(B,) if initial is not None else None)
         a.initial_index = int(initial_index)

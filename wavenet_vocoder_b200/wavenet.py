@@ -19,6 +19,7 @@ Conscious divergences from the reference (SURVEY.md 7 "quirks"):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -85,6 +86,7 @@ class WaveNet(nn.Module):
         self.receptive_field = receptive_field_size(layers, stacks, kernel_size)
         self._engine: Optional[SynthesisEngine] = None
         self._engine_key = None
+        self._native_upsample = False
 
     # ------------------------------------------------------------------ small API of the reference
     def has_speaker_embedding(self):
@@ -186,6 +188,8 @@ class WaveNet(nn.Module):
             self._engine_key = None
         if self._engine_key != key:
             self._engine.load_state_dict(self.state_dict())
+            # the upsample network runs on the device too when libwn covers its configuration
+            self._native_upsample = self._engine.load_upsampler(self.upsample_net)
             self._engine_key = key
         return self._engine
 
@@ -244,15 +248,22 @@ class WaveNet(nn.Module):
             if g_vec.size(0) == 1 and B > 1:
                 g_vec = g_vec.expand(B, -1)
             B = max(B, g_vec.size(0)) if c is None and test_inputs is None else B
+        c_frames = None
         if c is not None:
             c = c.to(dev).float()
-            if self.upsample_net is not None:
-                c = self.upsample_net(c)
-                assert c.size(-1) == T                                              # wavenet.py:276
-            if c.size(-1) == T:
-                c = c.transpose(1, 2)
-            c = c.contiguous()
-            assert c.size(1) == T and c.size(2) == self.cin_channels
+            if self.upsample_net is not None and getattr(self, "_native_upsample", False) \
+                    and os.environ.get("WN_TORCH_UPSAMPLE", "0") != "1":
+                assert c.dim() == 3 and c.size(1) == self.cin_channels
+                assert eng.upsampled_length(c.size(-1)) == T                        # wavenet.py:276
+                c_frames, c = c.contiguous(), None        # conv_in + stretch/smooth run inside libwn (csrc/wn_aux.cuh)
+            else:
+                if self.upsample_net is not None:
+                    c = self.upsample_net(c)
+                    assert c.size(-1) == T                                          # wavenet.py:276
+                if c.size(-1) == T:
+                    c = c.transpose(1, 2)
+                c = c.contiguous()
+                assert c.size(1) == T and c.size(2) == self.cin_channels
         initial = None
         initial_index = -1
         initial_rows = initial_dense = None
@@ -283,7 +294,7 @@ class WaveNet(nn.Module):
                 else:
                     initial_dense = first.contiguous()
         out, params = eng.generate(
-            B=B, T=T, c=c, g=g_vec, initial=initial, initial_index=initial_index,
+            B=B, T=T, c=c, c_frames=c_frames, g=g_vec, initial=initial, initial_index=initial_index,
             initial_rows=initial_rows, initial_dense=initial_dense,
             test_scalar=test_scalar, test_index=test_index, test_dense=test_dense,
             softmax=bool(softmax), quantize=bool(quantize), noise=noise, seed=seed,
