@@ -35,6 +35,29 @@ def dev_noise(n):
     return {k: v.cuda() for k, v in n.items()}
 
 
+TIE_MARGIN = 1e-4
+
+
+def assert_class_ids_match(idx_got, logits_ref, e_noise, what=""):
+    """Index work is bit-exact except at documented near-ties.  The sampled class of step t is
+    argmax_i (p_i / sum p) / e_i  (OneHotCategorical, wavenet.py:334-335) with p = softmax(logits).  The kernel's
+    logits differ from the reference's by ~1e-6 (summation order), so the winner can only change where the two
+    largest ratios are within TIE_MARGIN (relative).  Assert: every step whose top-2 margin is >= TIE_MARGIN has
+    the identical class id, and every differing step picked the reference's runner-up.
+    idx_got (B,T) int; logits_ref (B,O,T); e_noise (T,B,O)."""
+    p = torch.softmax(logits_ref.double(), dim=1)
+    r = (p / p.sum(1, keepdim=True)) / e_noise.permute(1, 2, 0).double()          # (B,O,T)
+    top = r.topk(2, dim=1)
+    margin = (top.values[:, 0] - top.values[:, 1]) / top.values[:, 0]              # (B,T)
+    ref_idx = top.indices[:, 0]
+    diff = idx_got.long() != ref_idx
+    clear = margin >= TIE_MARGIN
+    assert not bool((diff & clear).any()), "%s: %d class ids differ at steps with a clear margin (min margin there %.3g)" % (
+        what, int((diff & clear).sum()), float(margin[diff & clear].min()))
+    assert bool((idx_got.long()[diff] == top.indices[:, 1][diff]).all()), what + ": a near-tie resolved to a third class"
+    return int(diff.sum()), float(margin.min())
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_teacher_forced(name):
     gc = GoldenCase(name)
@@ -52,8 +75,8 @@ def test_golden_teacher_forced(name):
     else:
         assert y.shape == (gc.B, gc.cfg.out_channels, gc.T)
         assert float(y.sum(1).min()) == 1.0 and float(y.sum(1).max()) == 1.0          # one-hot
-        agree = (y.argmax(1).cpu() == gc.t("y_tf").long()).float().mean().item()
-        assert agree >= 0.98, agree
+        ndiff, _ = assert_class_ids_match(y.argmax(1).cpu(), ref, gc.noise_tf["e"], name)
+        assert (y.argmax(1).cpu() != gc.t("y_tf").long()).sum().item() == ndiff       # the fixture agrees with the rule
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -68,8 +91,18 @@ def test_golden_free_running_replayed_noise(name):
         rms = float(((y.cpu() - ref) ** 2).mean().sqrt())
         assert rms <= RMS_TOL, rms
     else:
-        agree = (y.argmax(1).cpu() == ref.long()).float().mean().item()
-        assert agree >= 0.98, agree
+        # free running: every step is checked on the kernel's OWN trajectory (teacher-force it into the oracle), so
+        # one near-tie cannot hide later mismatches; and up to the first divergence the fixture must agree exactly
+        got = y.argmax(1).cpu()
+        first = torch.zeros(gc.B_free, gc.cfg.out_channels, 1)
+        first[:, 127] = 1
+        ti = torch.cat([first, y.cpu()[:, :, :-1]], dim=2)
+        rec = []
+        orc.incremental_forward(gc.cfg, gc.w, test_inputs=ti, T=gc.T, softmax=False, quantize=False, params_out=rec)
+        ndiff, _ = assert_class_ids_match(got, torch.stack(rec, -1), gc.noise["e"], name + " (free running)")
+        same = (got == ref.long())
+        if ndiff == 0:
+            assert bool(same.all())
 
 
 def test_make_generation_fast_gives_same_result():
@@ -303,8 +336,14 @@ def test_full_width_configs_against_oracle(name):
         rms = float(((y.cpu() - y_ref) ** 2).mean().sqrt())
         assert rms <= RMS_TOL, rms
     else:
-        assert (y_tf.argmax(1).cpu() == y_ref.argmax(1)).float().mean().item() >= 0.97
-        assert (y.argmax(1).cpu() == y_ref.argmax(1)).float().mean().item() >= 0.9
+        assert_class_ids_match(y_tf.argmax(1).cpu(), p_ref, noise["e"], name)
+        first = torch.zeros(B, cfg.out_channels, 1)
+        first[:, 127] = 1
+        ti2 = torch.cat([first, y.cpu()[:, :, :-1]], dim=2)
+        rec2 = []
+        with torch.no_grad():
+            orc.incremental_forward(cfg, w, test_inputs=ti2, T=T, softmax=False, quantize=False, params_out=rec2)
+        assert_class_ids_match(y.argmax(1).cpu(), torch.stack(rec2, -1), noise["e"], name + " (free running)")
     print("%s: head-output max abs err %.3g" % (name, perr))
 
 
@@ -465,8 +504,14 @@ def test_initial_input_like_eval_model():
         y_ref = orc.incremental_forward(gc.cfg, gc.w, initial_input=init[r:r + 1], T=T,
                                         noise=orc.replay_from_predrawn(gc.cfg, nr))
         assert float(((y[r:r + 1].cpu() - y_ref) ** 2).mean().sqrt()) <= RMS_TOL
+    # test_inputs override step 0 (wavenet.py:299-301): initial_input is then unused, whatever its shape
+    n3 = orc.predraw_noise(gc.cfg, 3, 8, 6)
+    ya = m.incremental_forward(initial_input=init, test_inputs=torch.zeros(3, 1, 4), T=8, noise=dev_noise(n3))
+    yb = m.incremental_forward(test_inputs=torch.zeros(3, 1, 4), T=8, noise=dev_noise(n3))
+    assert torch.equal(ya, yb)
     with pytest.raises(ValueError):
-        m.incremental_forward(initial_input=init, test_inputs=torch.zeros(3, 1, 4), T=8, noise=dev_noise(noise))
+        m.incremental_forward(initial_input=torch.zeros(3, 1, 1), g=None, c=None, T=8,
+                              noise=dev_noise(orc.predraw_noise(gc.cfg, 2, 8, 6)))
     gq = GoldenCase("mulaw_softmax")
     mq = cuda_model(gq)
     Q = gq.cfg.out_channels
@@ -478,4 +523,204 @@ def test_initial_input_like_eval_model():
         yq = mq.incremental_forward(initial_input=init_q, T=32, noise=dev_noise(nz))
         yq_ref = orc.incremental_forward(gq.cfg, gq.w, initial_input=init_q, T=32,
                                          noise=orc.replay_from_predrawn(gq.cfg, nz))
-        assert (yq.argmax(1).cpu() == yq_ref.argmax(1)).float().mean().item() >= 0.95
+        ti = torch.cat([init_q.view(1, 1, Q).transpose(1, 2), yq.cpu()[:, :, :-1]], dim=2)
+        rec = []
+        orc.incremental_forward(gq.cfg, gq.w, test_inputs=ti, T=32, softmax=False, quantize=False, params_out=rec)
+        assert_class_ids_match(yq.argmax(1).cpu(), torch.stack(rec, -1), nz["e"], "initial_input " + layout)
+    # per-utterance one-hot start classes and a dense (non one-hot) start vector are fed as given (wavenet.py:281-292)
+    B2 = 3
+    oh = torch.zeros(B2, 1, Q)
+    for r, k in enumerate((5, 200, 77)):
+        oh[r, 0, k] = 1
+    nz = orc.predraw_noise(gq.cfg, B2, 24, 8)
+    for init_q in (oh, 0.7 * oh + 0.3 / Q):
+        p_got = mq.incremental_forward(initial_input=init_q, T=24, noise=dev_noise(nz), softmax=True, quantize=False)
+        for r in range(B2):
+            p_ref = orc.incremental_forward(gq.cfg, gq.w, initial_input=init_q[r:r + 1], T=24, softmax=True, quantize=False)
+            assert float((p_got[r:r + 1].cpu() - p_ref).abs().max()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# Batch tiles at BASELINE config 2's full width (what config 4 runs: 8 utterances per GPU in one launch), and a
+# wide stack whose blocks own several row quads per job
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [2, 4, 8])
+def test_config2_width_batch_tiles_against_oracle(B):
+    m, cfg, w, _ = full_case("cfg2_mol24")
+    T = 64
+    gen = torch.Generator().manual_seed(40 + B)
+    c = torch.randn(B, cfg.cin_channels, T, generator=gen)
+    noise = orc.predraw_noise(cfg, B, T, 50 + B)
+    rec = []
+    with torch.no_grad():
+        y_ref = orc.incremental_forward(cfg, w, c=c, T=T, noise=orc.replay_from_predrawn(cfg, noise), params_out=rec)
+    p_ref = torch.stack(rec, dim=-1)
+    mc = m.cuda()
+    assert mc._get_engine().plan(B)["batch_tile"] == B
+    ti = torch.cat([torch.zeros(B, 1, 1), y_ref[:, :, :-1]], dim=2)
+    y_tf, params = mc.incremental_forward(test_inputs=ti, c=c, T=T, noise=dev_noise(noise), return_params=True)
+    perr = float((params.cpu() - p_ref).abs().max())
+    assert perr <= PARAM_TOL * 2, perr
+    assert float((y_tf.cpu() - y_ref).abs().max()) <= 2e-4
+    y = mc.incremental_forward(c=c, T=T, noise=dev_noise(noise))
+    rms = float(((y.cpu() - y_ref) ** 2).mean().sqrt())
+    assert rms <= RMS_TOL, rms
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_wide_stack_several_quads_per_owner(B):
+    """R = 768, G/2 = 384: every block owns 3 gate pairs / 6 residual rows -> two row quads per job and owner, with
+    padding rows inside the quads (the widest layer whose per-block blob still double-buffers in shared memory)."""
+    from wavenet_vocoder_b200 import WaveNet
+    kw = dict(out_channels=30, layers=4, stacks=2, residual_channels=768, gate_channels=768, skip_out_channels=256,
+              cin_channels=80, gin_channels=-1, scalar_input=True, output_distribution="Logistic", dropout=0.0)
+    torch.manual_seed(21)
+    m = WaveNet(**kw).eval()
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if n_.endswith(".bias"):
+                p.normal_(0, 0.05)
+        m.last_conv_layers[3].bias[20:] -= 3.0
+    cfg = orc.PathConfig(out_channels=30, layers=4, stacks=2, residual_channels=768, gate_channels=768,
+                         skip_out_channels=256, kernel_size=3, cin_channels=80, gin_channels=-1, scalar_input=True,
+                         output_distribution="Logistic")
+    w = orc.weights_from_state_dict(cfg, {k: v.detach().clone() for k, v in m.state_dict().items()})
+    T = 40
+    gen = torch.Generator().manual_seed(3)
+    c = torch.randn(B, 80, T, generator=gen)
+    noise = orc.predraw_noise(cfg, B, T, 4)
+    rec = []
+    with torch.no_grad():
+        y_ref = orc.incremental_forward(cfg, w, c=c, T=T, noise=orc.replay_from_predrawn(cfg, noise), params_out=rec)
+    mc = m.cuda()
+    plan = mc._get_engine().plan(B)
+    assert plan["rows_y"] == 3 and plan["rows_x"] == 6
+    ti = torch.cat([torch.zeros(B, 1, 1), y_ref[:, :, :-1]], dim=2)
+    _, params = mc.incremental_forward(test_inputs=ti, c=c, T=T, noise=dev_noise(noise), return_params=True)
+    assert float((params.cpu() - torch.stack(rec, -1)).abs().max()) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# The TIMED path draws its noise on the device (Philox4x32-10 -> uniform / Box-Muller): its distribution against the
+# oracle's sampler (torch RNG) on FIXED head outputs.  A model whose head output is a constant vector (all weights of the
+# last 1x1 zero, the parameters in its bias) makes every step an independent draw from the same distribution.
+# ------------------------------------------------------------------------------------------------
+def const_head_model(kw, bias):
+    from wavenet_vocoder_b200 import WaveNet
+    torch.manual_seed(0)
+    m = WaveNet(**kw).eval()
+    with torch.no_grad():
+        m.last_conv_layers[3].weight_g.mul_(0)        # w = g * v / |v| = 0
+        m.last_conv_layers[3].bias.copy_(bias)
+    return m.cuda()
+
+
+def ks_two_sample(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    ca = np.searchsorted(a, allv, side="right") / a.size
+    cb = np.searchsorted(b, allv, side="right") / b.size
+    return float(np.abs(ca - cb).max())
+
+
+def test_philox_mol_draws_follow_the_reference_sampler():
+    K = 10
+    kw = dict(out_channels=3 * K, layers=2, stacks=1, residual_channels=8, gate_channels=16, skip_out_channels=8,
+              scalar_input=True, output_distribution="Logistic", dropout=0.0)
+    gen = torch.Generator().manual_seed(1)
+    logits = torch.randn(K, generator=gen)
+    means = torch.linspace(-0.6, 0.6, K)
+    log_scales = torch.full((K,), -5.5) + 0.3 * torch.randn(K, generator=gen)
+    bias = torch.cat([logits, means, log_scales])
+    m = const_head_model(kw, bias)
+    B, T = 8, 25000                                                   # 2e5 independent draws
+    y, params = m.incremental_forward(T=T, seed=123, initial_input=torch.zeros(B, 1, 1), return_params=True)
+    assert float((params[:, :, ::997].cpu() - bias.view(1, -1, 1)).abs().max()) <= 1e-6      # the head really is constant
+    got = y.reshape(-1).cpu().numpy()
+    torch.manual_seed(5)
+    n = got.size
+    ref = orc.sample_mol(bias.view(1, 1, -1).expand(n, 1, -1).contiguous(), orc.GlobalNoise()).reshape(-1).numpy()
+    # (a) component frequencies: nearest mean identifies the component (means are 0.13 apart, scales ~0.004)
+    pick = lambda v: np.abs(v[:, None] - means.numpy()[None, :]).argmin(1)
+    f_got = np.bincount(pick(got), minlength=K) / n
+    f_ref = np.bincount(pick(ref), minlength=K) / n
+    p_true = torch.softmax(logits, 0).numpy()
+    sigma = np.sqrt(p_true * (1 - p_true) / n)
+    assert np.all(np.abs(f_got - p_true) <= 5 * sigma + 2e-3), (f_got, p_true)
+    assert np.all(np.abs(f_got - f_ref) <= 7 * sigma + 2e-3)
+    # (b) moments and (c) Kolmogorov-Smirnov distance between the two samples (critical value 1.95*sqrt(2/n) at 1e-3)
+    assert abs(got.mean() - ref.mean()) <= 5 * ref.std() / np.sqrt(n) * np.sqrt(2)
+    assert abs(got.var() / ref.var() - 1.0) <= 0.02
+    assert ks_two_sample(got, ref) <= 1.95 * np.sqrt(2.0 / n) * 1.5
+
+
+def test_philox_gaussian_and_categorical_draws():
+    # single Gaussian: Box-Muller normal vs torch normal
+    kw = dict(out_channels=2, layers=2, stacks=1, residual_channels=8, gate_channels=16, skip_out_channels=8,
+              scalar_input=True, output_distribution="Normal", dropout=0.0)
+    bias = torch.tensor([0.1, -2.0])
+    m = const_head_model(kw, bias)
+    B, T = 8, 25000
+    got = m.incremental_forward(T=T, seed=9, initial_input=torch.zeros(B, 1, 1)).reshape(-1).cpu().numpy()
+    n = got.size
+    sd = float(np.exp(-2.0))
+    assert abs(got.mean() - 0.1) <= 5 * sd / np.sqrt(n)
+    assert abs(got.std() / sd - 1.0) <= 0.01
+    torch.manual_seed(2)
+    ref = (torch.randn(n) * sd + 0.1).clamp(-1, 1).numpy()
+    assert ks_two_sample(got, ref) <= 1.95 * np.sqrt(2.0 / n) * 1.5
+    # categorical (softmax head): class frequencies vs the probabilities
+    Q = 16
+    kwq = dict(out_channels=Q, layers=2, stacks=1, residual_channels=8, gate_channels=16, skip_out_channels=8,
+               scalar_input=False, dropout=0.0)
+    logits = torch.randn(Q, generator=torch.Generator().manual_seed(3))
+    mq = const_head_model(kwq, logits)
+    init = torch.zeros(B, 1, Q)
+    init[:, :, 0] = 1
+    yq = mq.incremental_forward(T=T, seed=4, initial_input=init)
+    idx = yq.argmax(1).reshape(-1).cpu().numpy()
+    f = np.bincount(idx, minlength=Q) / idx.size
+    p = torch.softmax(logits, 0).numpy()
+    assert np.all(np.abs(f - p) <= 5 * np.sqrt(p * (1 - p) / idx.size) + 1e-3), (f, p)
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-length runs with a strided oracle check: the kernel free-runs T samples (device noise, the timed path); windows
+# of its OWN output are then teacher-forced into the oracle, preceded by one receptive field of history so that the
+# oracle's zero-initialised queues have forgotten their start, and the head outputs of the window are compared.
+# ------------------------------------------------------------------------------------------------
+def strided_oracle_check(name, T, starts, win, tol):
+    m, cfg, w, _ = full_case(name)
+    rf = orc.receptive_field_size(cfg.layers, cfg.stacks, cfg.kernel_size)
+    gen = torch.Generator().manual_seed(6)
+    c = torch.randn(1, cfg.cin_channels, T, generator=gen)
+    mc = m.cuda()
+    y, params = mc.incremental_forward(c=c, T=T, seed=31, return_params=True)
+    y, params = y.cpu(), params.cpu()
+    assert bool(torch.isfinite(y).all()) and float(y.abs().max()) <= 1.0 and float(y.std()) > 1e-3
+    worst = 0.0
+    for t0 in starts:
+        a = max(0, t0 - rf)                                        # oracle starts here with empty queues
+        b = min(T, t0 + win)
+        # input of step t is the sample of step t-1 (0 at t=0)
+        prev = torch.cat([torch.zeros(1, 1, 1), y[:, :, :-1]], dim=2)[:, :, a:b]
+        rec = []
+        with torch.no_grad():
+            orc.incremental_forward(cfg, w, test_inputs=prev, c=c[:, :, a:b], T=b - a,
+                                    noise=orc.replay_from_predrawn(cfg, orc.predraw_noise(cfg, 1, b - a, 1)),
+                                    params_out=rec)
+        p_ref = torch.stack(rec, dim=-1)
+        lo = t0 - a if a > 0 else 0
+        err = float((params[:, :, a + lo:b] - p_ref[:, :, lo:]).abs().max())
+        worst = max(worst, err)
+        assert err <= tol, (name, t0, err)
+    print("%s: strided oracle check over %d windows, worst head-output error %.3g" % (name, len(starts), worst))
+
+
+def test_config2_full_length_strided_oracle():
+    strided_oracle_check("cfg2_mol24", 22050, [0, 11000, 22050 - 256], 256, 2e-5 * 2.5)
+
+
+def test_config5_long_form_strided_oracle():
+    """BASELINE config 5: T = 240 000 (10 s at 24 kHz): tag arithmetic, 234 wraps of the largest history ring."""
+    strided_oracle_check("cfg5_mol30", 240000, [0, 239000], 192, 2e-5 * 2.5)
