@@ -682,7 +682,7 @@ struct Engine {
                 const int g = __float_as_int(tab[k]);
                 v = 0.f;
                 if (g >= 0) {
-                    const int idx = s_idx[b];
+                    const int idx = min(s_idx[b], O - 1);          // class ids are range-checked on the host where it can
                     if (idx >= 0) {
                         v = __ldg(pp.first_w + (size_t)idx * R + g) + tab[kk + k];   // one-hot input: a column gather
                     } else {

@@ -800,7 +800,17 @@ static int32_t launch_chunk6(WnHandle* h, const wn_generate_args* a, int b0, int
     }
     lc.attrs = la;
     lc.numAttrs = na;
-    CUDA_TRY(cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs));
+    cudaError_t le = cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs);
+    if (le != cudaSuccess && h->coop_with_clusters) {
+        // some driver / runtime combinations refuse the cooperative attribute together with a cluster dimension:
+        // fall back to a plain cluster launch (the grid never exceeds the co-resident cluster count the occupancy
+        // query reported at wn_create, so the blocks are co-resident on an otherwise idle GPU)
+        cudaGetLastError();
+        lc.numAttrs = 1;
+        le = cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs);
+        if (le == cudaSuccess) h->coop_with_clusters = false;
+    }
+    if (le != cudaSuccess) return fail(WN_ERR_CUDA, std::string("cudaLaunchKernelExC: ") + cudaGetErrorString(le));
     h->launches++;
     return WN_OK;
 }
