@@ -69,7 +69,7 @@ typedef struct wn_config {
     int32_t num_ctas;             /* 0 = choose; else number of cooperating thread blocks */
     int32_t exchange_copies;      /* 0 = choose; replicas of each exchange vector in L2   */
     int32_t ring_slots;           /* 0 = choose; streaming weight slots in shared memory  */
-    int32_t cluster_size;         /* 0 = choose; thread blocks per cluster (power of two <= 16) */
+    int32_t poll_warps;           /* 0 = choose; warps that poll the exchange into shared memory (2..12) */
     int32_t reserved[7];
 } wn_config;
 
@@ -143,8 +143,8 @@ typedef struct wn_plan_info {
     int64_t launches;                  /* kernels launched by this handle so far             */
     int64_t cond_packed_bytes_per_cta; /* size of the conditioning-weight image of one block */
     int64_t bias_packed_bytes_per_cta; /* size of the bias image of one block (cluster engine) */
-    int64_t num_clusters, cluster_size, num_passes, engine;
-    int64_t reserved[1];
+    int64_t num_clusters, cluster_size, num_passes, engine;   /* clusters are not used by the current engine: P, 1 */
+    int64_t poll_warps;
 } wn_plan_info;
 
 int32_t wn_abi_version(void);
@@ -201,14 +201,14 @@ int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out);
  * packed weight image of thread block `cta` into `packed`: packed_bytes_per_cta bytes (layer
  * blobs + head blob) followed, if the buffer has room, by cond_packed_bytes_per_cta bytes (the
  * local-conditioning rows the conditioning warp reads from L2) and bias_packed_bytes_per_cta bytes
- * (biases of the rows the block finalises). */
+ * (biases of the rows the block owns). */
 int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
                      wn_plan_info* out);
 int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
                     const wn_weights* w, int32_t cta, float* packed, int64_t packed_floats);
 
-/* Cluster engine only: the raw execution plan (struct Wn6Plan of csrc/wn6_plan.h as int32 words) and its pass
- * table (struct Wn6Pass, 20 bytes each), for tools and the host tests that replay the packed image.
+/* The raw execution plan (struct Wn7Plan of csrc/wn7_plan.h as int32 words) and its pass table (struct Wn7Pass,
+ * 12 bytes each), for tools and the host tests that replay the packed image.
  * Returns the number of passes (>= 0) or a negative wn_status. */
 int32_t wn_plan_passes(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta,
                        int32_t* plan_words, int32_t max_plan_words, void* passes, int32_t max_passes);

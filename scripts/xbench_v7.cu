@@ -45,12 +45,15 @@ __device__ int g_abort = 0;
 // pair index of element k of a stage slot: `spread` = 0 contiguous, else 4 pairs (one 32-byte sector) per 256-byte
 // granule so that the 192 sectors of a stage land on as many L2 slices as possible
 __device__ __forceinline__ long long pidx(int k, int spread) {
-    return spread ? (long long)(k >> 2) * 32 + (k & 3) : (long long)k;
+    if (spread == 1) return (long long)(k >> 2) * 32 + (k & 3);        // 4 pairs (32 B) per 256-byte granule
+    if (spread == 2) return (long long)(k >> 1) * 16 + (k & 1);        // 2 pairs (16 B) per 128-byte line
+    if (spread == 3) return (long long)(k >> 3) * 32 + (k & 7);        // 8 pairs (64 B) per 256-byte granule
+    return (long long)k;
 }
 
 template <int NPOLL>
 __global__ void __launch_bounds__(32 * (NPOLL + NCOMP), 1)
-xv7(uint2* buf, long long slot_pairs, int rounds, int spread, long long* out, float* check) {
+xv7(uint2* buf, long long slot_pairs, int rounds, int spread, int gate_delay, int backoff_ns, int lane_arrive, long long* out, float* check) {
     constexpr int NPL = 32 * NPOLL;           // polling lanes
     constexpr int NLD = KTOT / 2;             // 16-byte loads per stage
     __shared__ __align__(16) float xin[2][KTOT];
@@ -59,7 +62,7 @@ xv7(uint2* buf, long long slot_pairs, int rounds, int spread, long long* out, fl
     __shared__ long long t_pub_s, t_wake_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, p = blockIdx.x;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_in[i], NPL); mbar_init(&bar_free[i], NCOMP); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_in[i], lane_arrive ? NPL : NPOLL); mbar_init(&bar_free[i], NCOMP); }
         t_pub_s = 0; t_wake_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -70,10 +73,12 @@ xv7(uint2* buf, long long slot_pairs, int rounds, int spread, long long* out, fl
     float v_final = 0.f;
     if (warp < NPOLL) {
         const int pl = warp * 32 + lane;
-        const int own_lane = (6 * p / 2) % NPL;      // the lane whose first load covers this block's first value
+        long long t_prev = clock64();
         for (int r = 0; r < rounds; ++r) {
             const int par = r & 1, use = r >> 1;
             if (use > 0) { const long long tw = clock64(); while (!mbar_try_wait(&bar_free[par], (use - 1) & 1)) { WATCHDOG(tw) } }
+            // gate: the next vector cannot be complete earlier than `gate_delay` cycles after the previous one was
+            if (gate_delay > 0 && r > 0) { while (clock64() - t_prev < gate_delay) {} }
             const long long tw = clock64();
             for (int j = pl; j < NLD; j += NPL) {
                 float v0, v1;
@@ -83,15 +88,16 @@ xv7(uint2* buf, long long slot_pairs, int rounds, int spread, long long* out, fl
                     const uint2* src = buf + (long long)((r - 1) % NSLOT) * slot_pairs + pidx(2 * j, spread);
                     uint4 q;
                     int tries = 0;
-                    while (true) { q = ld_pair2(src); ++tries; if (q.y == tag && q.w == tag) break; WATCHDOG(tw) }
+                    while (true) { q = ld_pair2(src); ++tries; if (q.y == tag && q.w == tag) break; if (backoff_ns > 0) __nanosleep(backoff_ns); WATCHDOG(tw) }
                     if (j == 6 * p / 2) { acc_own += clock64() - t_pub_s; acc_poll1 += tries; }
                     v0 = __uint_as_float(q.x); v1 = __uint_as_float(q.z);
                 }
                 *reinterpret_cast<float2*>(&xin[par][2 * j]) = make_float2(v0, v1);
             }
-            mbar_arrive(&bar_in[par]);
+            t_prev = clock64();
+            if (lane_arrive) mbar_arrive(&bar_in[par]);
+            else { __syncwarp(); if (lane == 0) mbar_arrive(&bar_in[par]); }
         }
-        (void)own_lane;
     } else {
         const int cw = warp - NPOLL;
         const bool gate_rows = cw < 2;
@@ -157,10 +163,10 @@ xv7(uint2* buf, long long slot_pairs, int rounds, int spread, long long* out, fl
 }
 
 template <int NPOLL>
-static void run(uint2* buf, long long slot_pairs, long long* out, float* check, int rounds, int spread) {
+static void run(uint2* buf, long long slot_pairs, long long* out, float* check, int rounds, int spread, int gate_delay, int backoff_ns, int lane_arrive) {
     cudaMemset(buf, 0, (size_t)NSLOT * slot_pairs * sizeof(uint2));
     cudaMemset(out, 0, 128 * 8 * sizeof(long long));
-    void* args[] = {&buf, &slot_pairs, &rounds, &spread, &out, &check};
+    void* args[] = {&buf, &slot_pairs, &rounds, &spread, &gate_delay, &backoff_ns, &lane_arrive, &out, &check};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)xv7<NPOLL>, dim3(128), dim3(32 * (NPOLL + NCOMP)), args, 0, 0);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess) { printf("NPOLL=%d: launch failed %s / %s\n", NPOLL, cudaGetErrorString(e), cudaGetErrorString(e2)); cudaGetLastError(); return; }
@@ -174,8 +180,8 @@ static void run(uint2* buf, long long slot_pairs, long long* out, float* check, 
         mx = h[i * 8] > mx ? h[i * 8] : mx; se += h[i * 8 + 1]; sl += h[i * 8 + 2]; so += h[i * 8 + 3]; st += h[i * 8 + 4];
         if (hc[i] != (float)(rounds + 1)) ++bad;
     }
-    printf("poll warps=%2d (%.1f loads/lane) spread=%d : %6.0f cycles/stage | exchange (publish->awake) %6.0f  local (awake->publish) %5.0f | own value visible after %6.0f cycles, %.2f polls  wrong=%d\n",
-           NPOLL, 384.0 / (32 * NPOLL), spread, (double)mx / rounds, se / 128 / rounds, sl / 128 / rounds, so / 128 / rounds, st / 128 / rounds, bad);
+    printf("poll warps=%2d (%.1f loads/lane) spread=%d gate=%4d backoff=%3d lane_arrive=%d : %6.0f cycles/stage | exchange (publish->awake) %6.0f  local (awake->publish) %5.0f | own value visible after %6.0f cycles, %.2f polls  wrong=%d\n",
+           NPOLL, 384.0 / (32 * NPOLL), spread, gate_delay, backoff_ns, lane_arrive, (double)mx / rounds, se / 128 / rounds, sl / 128 / rounds, so / 128 / rounds, st / 128 / rounds, bad);
 }
 
 int main() {
@@ -185,14 +191,18 @@ int main() {
     cudaMalloc(&buf, (size_t)NSLOT * slot_pairs * sizeof(uint2));
     cudaMalloc(&out, 128 * 8 * sizeof(long long));
     cudaMalloc(&check, 128 * sizeof(float));
-    const int rounds = 20000;
-    for (int rep = 0; rep < 2; ++rep)
-        for (int spread = 0; spread < 2; ++spread) {
-            run<12>(buf, slot_pairs, out, check, rounds, spread);
-            run<8>(buf, slot_pairs, out, check, rounds, spread);
-            run<6>(buf, slot_pairs, out, check, rounds, spread);
-            run<4>(buf, slot_pairs, out, check, rounds, spread);
-            run<2>(buf, slot_pairs, out, check, rounds, spread);
-        }
+    const int rounds = 6000;
+    // 1. arrive per lane vs per warp
+    for (int la : {1, 0}) { run<12>(buf, slot_pairs, out, check, rounds, 1, 0, 0, la); run<4>(buf, slot_pairs, out, check, rounds, 1, 0, 0, la); }
+    // 2. layouts
+    for (int sp : {0, 1, 2, 3}) { run<12>(buf, slot_pairs, out, check, rounds, sp, 0, 0, 0); run<4>(buf, slot_pairs, out, check, rounds, sp, 0, 0, 0); }
+    // 3. gating delay and back-off between attempts
+    for (int sp : {1, 3})
+        for (int gd : {0, 800, 1200, 1600, 2000, 2400})
+            for (int bo : {0, 100}) {
+                run<12>(buf, slot_pairs, out, check, rounds, sp, gd, bo, 0);
+                run<8>(buf, slot_pairs, out, check, rounds, sp, gd, bo, 0);
+                run<4>(buf, slot_pairs, out, check, rounds, sp, gd, bo, 0);
+            }
     return 0;
 }

@@ -80,7 +80,7 @@ def test_plan_numbers_match_survey_table():
                        output_distribution="Normal")
     p3 = plan_of(cfg3)
     assert p3["flops_per_sample"] == 7308032 + 2 * 24 * 256 * 0   # Wg.g is folded once per call
-    assert p3["resident_blobs"] >= 16 and p3["smem_bytes"] <= SMEM
+    assert p3["resident_blobs"] >= 12 and p3["smem_bytes"] <= SMEM
     cfg1 = make_config(layers=12, stacks=2, residual_channels=64, gate_channels=128, skip_out_channels=64,
                        out_channels=256, kernel_size=3, cin_channels=-1, gin_channels=-1, scalar_input=False,
                        output_distribution="Logistic")
@@ -111,42 +111,37 @@ def test_planner_rejects_bad_shapes():
 
 
 # ------------------------------------------------------------------------------------------------
-# independent reading of the packed layout (documented in csrc/wn6_plan.h / DESIGN.md)
+# independent reading of the packed layout (documented in csrc/wn7_plan.h / DESIGN.md)
 # ------------------------------------------------------------------------------------------------
 def part(rows, n, p):
     q, r = divmod(rows, n)
     return p * q + min(p, r), q + (1 if p < r else 0)
 
 
-def own(rows, NC, CS, c, r):
-    cb, cc = part(rows, NC, c)
-    ob, oc = part(cc, CS, r)
-    return cb + ob, oc
-
-
 K_FIRST, K_LAYER, K_TAIL, K_HEAD1, K_HEAD2 = range(5)
+J_A0, J_A, J_B, J_D, J_S, J_SL, J_HA, J_HB = range(8)
 
 
 class PackedModel:
-    """Replays the cluster engine's dataflow from the packed per-block images with its own arithmetic:
-    K-slices gathered from the values the rank-r blocks of all clusters published, pass tiles
-    [j][lane][4 rows] multiplied with the slice (k = x_off + sub + 16 j), partial sums summed by the row
-    owners in rank order, then bias / conditioning / queued taps / gate / residual exactly as the finaliser
-    warps do."""
+    """Replays the kernel's dataflow from the packed per-block images with its own arithmetic: every pass is two rows
+    whose tile [j][row][lane][4 k] is multiplied with the stage vector (k = x_off + 4 (lane + 32 j) + 0..3; vector
+    order [y | pad | x] for the layer stages), then finalised exactly as the lanes of the compute warps do (bias,
+    conditioning, queued taps, gate, residual, skip accumulation, head)."""
 
-    def __init__(self, gc, P, cluster=0):
+    def __init__(self, gc, P):
         cfg = cfg_for(gc, num_ctas=P)
-        cfg.cluster_size = cluster
         self.gc, self.cfg = gc, cfg
         pl, passes = N.plan_passes(cfg, 1, NSM, SMEM)
-        assert pl.P == P and pl.NC * pl.CS == P
+        assert pl.P == P
         self.pl, self.passes = pl, passes
         info = plan_of(cfg)
-        assert info["num_ctas"] == P and info["num_clusters"] == pl.NC and info["cluster_size"] == pl.CS
-        assert info["engine"] == 6 and info["num_passes"] == len(passes)
+        assert info["num_ctas"] == P and info["engine"] == 7 and info["num_passes"] == len(passes)
         c = gc.cfg
         self.L, self.R, self.G2, self.S, self.O = c.layers, c.residual_channels, c.gate_channels // 2, c.skip_out_channels, c.out_channels
         self.kw, self.C = c.kernel_size, max(c.cin_channels, 0)
+        cdiv = lambda a, b: -(-a // b)
+        assert (info["rows_y"], info["rows_x"], info["rows_skip"]) == (cdiv(self.G2, P), pl.mx, pl.ms)
+        assert pl.mx == 2 * cdiv(cdiv(self.R, P), 2) and pl.xoff == 4 * cdiv(self.G2, 4)
         nmain, ncond, nbias = pl.cta_w_floats, pl.cta_cw_floats, pl.cta_b_floats
         assert info["packed_bytes_per_cta"] == 4 * nmain and info["cond_packed_bytes_per_cta"] == 4 * ncond
         assert info["bias_packed_bytes_per_cta"] == 4 * nbias
@@ -167,36 +162,30 @@ class PackedModel:
         n = pl.fb_floats if i == 0 else (pl.lb_floats if i < self.L else pl.tb_floats)
         return self.img[p]["w"][off:off + n]
 
-    def run_stage(self, kind, stage, xin):
-        """xin[r]: the K-slice of rank r (values).  Returns the partial sums [P][row][src rank] sent to the three
-        finaliser warps of every owner: (F0: gate / skip / head rows, DF: deferred rows, F1: residual rows)."""
+    def run_stage(self, kind, stage, vec):
+        """vec: the stage input vector in xin order.  Returns per block a list of (pass, [sum row 0, sum row 1])."""
         pl = self.pl
-        crit = np.zeros((pl.P, pl.nrow_c, pl.CS), np.float32)
-        defer = np.zeros((pl.P, pl.nrow_d, pl.CS), np.float32)
-        resid = np.zeros((pl.P, max(pl.nrow_x, 1), pl.CS), np.float32)
+        x = np.zeros(pl.xin_vals, np.float32)
+        x[:len(vec)] = vec
+        res = []
         for p in range(pl.P):
-            c, r = divmod(p, pl.CS)
             blob = self.blob(p, stage)
-            x = np.zeros(pl.xin_vals + 64, np.float32)
-            x[:len(xin[r])] = xin[r]
+            out = []
             for wv in range(8):
                 b0 = pl.pass_begin[kind][wv]
                 for ps in self.passes[b0:b0 + pl.pass_count[kind][wv]]:
-                    tile = blob[ps.w_off:ps.w_off + ps.nit * 128].reshape(ps.nit, 32, 4)
-                    for g in range(2):
-                        if ps.owner[g] < 0:
-                            continue
-                        ks = ps.x_off + np.arange(16)[None, :] + 16 * np.arange(ps.nit)[:, None]       # (nit, 16)
-                        sums = np.einsum("jsi,js->i", tile[:, g * 16:(g + 1) * 16, :].astype(np.float64), x[ks].astype(np.float64))
-                        dst = (crit, defer, resid)[ps.dst]
-                        dst[c * pl.CS + ps.owner[g], ps.dst_row[g]:ps.dst_row[g] + 4, r] = sums.astype(np.float32)
-        return crit, defer, resid
+                    tile = blob[ps.w_off:ps.w_off + ps.nit * 256].reshape(ps.nit, 2, 32, 4)
+                    ks = ps.x_off + 4 * (np.arange(32)[None, :, None] + 32 * np.arange(ps.nit)[:, None, None]) + np.arange(4)[None, None, :]
+                    sums = np.einsum("jrlk,jlk->r", tile.astype(np.float64), x[ks].astype(np.float64)).astype(np.float32)
+                    out.append((ps, sums))
+            res.append(out)
+        return res
 
     def run_teacher_forced(self, b):
         gc, pl, L, kw = self.gc, self.pl, self.L, self.kw
-        NC, CS, P = pl.NC, pl.CS, pl.P
+        P = pl.P
         G2, R, S, O = self.G2, self.R, self.S, self.O
-        my, mx, ms, mo, qA, qB, qD, qS = pl.my, pl.mx, pl.ms, pl.mo, pl.qA, pl.qB, pl.qD, pl.qS
+        my, mx, ms, qA, xoff = pl.my, pl.mx, pl.ms, pl.qA, pl.xoff
         w = gc.w
         T = gc.T
         dil = gc.cfg.dilations()
@@ -210,111 +199,102 @@ class PackedModel:
         rings = [[{tap: np.zeros(((kw - 1 - tap) * dil[l], 2 * my), np.float32) for tap in range(kw - 1)}
                   for l in range(L)] for _ in range(P)]
         out = np.zeros((O, T), np.float32)
+        own = [dict(y=part(G2, P, p), x=part(R, P, p), s=part(S, P, p), a=part(S, P, p), b=part(O, P, p)) for p in range(P)]
 
-        def slices(vec_parts):
-            """vec_parts: list of (published values per block [P][m], m); -> per-rank slices [c][m] concatenated"""
-            res = []
-            for r in range(CS):
-                segs = []
-                for vals, m in vec_parts:
-                    segs.append(np.concatenate([vals[c * CS + r][:m] for c in range(NC)]))
-                res.append(np.concatenate(segs))
-            return res
-
-        def x0_block(r):
-            v = np.zeros(NC * mx, np.float32)
-            for c in range(NC):
-                base, cnt = own(R, NC, CS, c, r)
-                v[c * mx:c * mx + cnt] = x0[base:base + cnt]
-            return v
+        def pre_of(p, l, t):
+            bias = self.img[p]["b"]
+            y0, ny = own[p]["y"]
+            pre = bias[pl.bo_zb + l * 2 * my: pl.bo_zb + (l + 1) * 2 * my].copy()
+            for j in range(ny):
+                if gb is not None:
+                    pre[2 * j] += gb[l][y0 + j]
+                    pre[2 * j + 1] += gb[l][G2 + y0 + j]
+            if self.C:
+                cw = self.img[p]["cw"][l * qA * self.C * 4:(l + 1) * qA * self.C * 4].reshape(qA, self.C, 4)
+                cw = cw.transpose(0, 2, 1).reshape(4 * qA, self.C)[:2 * my]
+                pre += cw @ c_up[b, :, t].numpy()
+            for tap in range(kw - 1):
+                pre += rings[p][l][tap][t % ((kw - 1 - tap) * dil[l])]
+            return pre
 
         for t in range(T):
-            x0 = first_w @ x_tf[:, t] + first_b
-            ypub = np.zeros((P, my), np.float32)
-            xpub = np.zeros((P, mx), np.float32)
-            for p in range(P):
-                c, r = divmod(p, CS)
-                base, cnt = own(R, NC, CS, c, r)
-                xpub[p, :cnt] = x0[base:base + cnt]
+            x_prev = (first_w @ x_tf[:, t] + first_b).astype(np.float32)
+            y_prev = np.zeros(G2, np.float32)
             skipacc = np.zeros((P, ms), np.float32)
-            for s_ in range(0, L):
-                kind = K_FIRST if s_ == 0 else K_LAYER
-                if s_ == 0:
-                    xin = [np.concatenate([np.zeros(NC * my, np.float32), x0_block(r)]) for r in range(CS)]
-                else:
-                    xin = slices([(ypub, my), (xpub, mx)])
-                    for r in range(CS):
-                        assert len(xin[r]) == pl.Ky + pl.Kx
-                crit, defer, resid = self.run_stage(kind, s_, xin)
-                ynew = np.zeros((P, my), np.float32)
-                xnew = np.zeros((P, mx), np.float32)
+            for s_ in range(0, L + 1):
+                kind = K_FIRST if s_ == 0 else (K_LAYER if s_ < L else K_TAIL)
+                vec = np.zeros(xoff + R, np.float32)
+                vec[:G2] = y_prev
+                vec[xoff:xoff + R] = x_prev
+                res = self.run_stage(kind, s_, vec)
+                y_new, x_new = np.zeros(G2, np.float32), x_prev.copy()
+                sk = np.zeros(S, np.float32)
                 for p in range(P):
-                    c, r = divmod(p, CS)
                     bias = self.img[p]["b"]
-                    y0, ny = own(G2, NC, CS, c, r)
-                    pre = bias[pl.bo_zb + s_ * 4 * qA: pl.bo_zb + s_ * 4 * qA + 2 * my].copy()
-                    for j in range(ny):
-                        if gb is not None:
-                            pre[2 * j] += gb[s_][y0 + j]
-                            pre[2 * j + 1] += gb[s_][G2 + y0 + j]
-                    if self.C:
-                        cw = self.img[p]["cw"][s_ * qA * self.C * 4:(s_ + 1) * qA * self.C * 4].reshape(qA, self.C, 4)
-                        cw = cw.transpose(0, 2, 1).reshape(4 * qA, self.C)[:2 * my]
-                        pre += cw @ c_up[b, :, t].numpy()
-                    for tap in range(kw - 1):
-                        pre += rings[p][s_][tap][t % ((kw - 1 - tap) * dil[s_])]
-                    z = crit[p, :2 * my].sum(axis=1) + pre
-                    for j in range(ny):
-                        ynew[p, j] = np.tanh(z[2 * j]) / (1.0 + np.exp(-z[2 * j + 1]))
+                    y0, ny = own[p]["y"]
+                    x0, nx = own[p]["x"]
+                    s0, ns = own[p]["s"]
+                    pre = pre_of(p, s_, t) if s_ < L else None
+                    for ps, v in res[p]:
+                        if ps.job in (J_A0, J_A):
+                            i = ps.idx
+                            if i < ny:
+                                za, zb = v[0] + pre[2 * i], v[1] + pre[2 * i + 1]
+                                y_new[y0 + i] = np.tanh(za) / (1.0 + np.exp(-zb))
+                        elif ps.job == J_B:
+                            for r in range(2):
+                                j = ps.idx + r
+                                if j < nx:
+                                    x_new[x0 + j] = (v[r] + bias[pl.bo_xb + s_ * mx + j] + x_prev[x0 + j]) * rs2
+                        elif ps.job == J_D:
+                            tap, i = divmod(ps.idx, my)
+                            D = (kw - 1 - tap) * dil[s_ - 1]
+                            rings[p][s_ - 1][tap][t % D][2 * i:2 * i + 2] = v
+                        elif ps.job == J_S:
+                            for r in range(2):
+                                j = ps.idx + r
+                                if j < ns:
+                                    h = v[r] + bias[pl.bo_sb + (s_ - 1) * ms + j]
+                                    skipacc[p, j] = h if s_ == 1 else skipacc[p, j] + h
+                        elif ps.job == J_SL:
+                            for r in range(2):
+                                j = ps.idx + r
+                                if j < ns:
+                                    tot = v[r] + bias[pl.bo_sb + (L - 1) * ms + j]
+                                    if L >= 2:
+                                        tot = skipacc[p, j] + tot
+                                    sk[s0 + j] = max(tot * np.float32(math.sqrt(1.0 / L)), 0)
+                        else:
+                            raise AssertionError(ps.job)
+                if s_ < L:
+                    y_prev = y_new
                     if s_ >= 1:
-                        x0r, nx = own(R, NC, CS, c, r)
-                        o = resid[p, :mx].sum(axis=1) + bias[pl.bo_xb + s_ * 4 * qB: pl.bo_xb + s_ * 4 * qB + mx]
-                        xnew[p, :nx] = ((o + xpub[p]) * rs2)[:nx]
-                        layer = s_ - 1
-                        for tap in range(kw - 1):
-                            D = (kw - 1 - tap) * dil[layer]
-                            rings[p][layer][tap][t % D] = defer[p, tap * 2 * my:(tap + 1) * 2 * my].sum(axis=1)
-                        h = defer[p, 4 * qD:4 * qD + ms].sum(axis=1) + bias[pl.bo_sb + layer * 4 * qS: pl.bo_sb + layer * 4 * qS + ms]
-                        skipacc[p] = h if layer == 0 else skipacc[p] + h
-                ypub = ynew
-                if s_ >= 1:
-                    xpub = xnew
-            # stage L: skip of the last layer
-            xin = slices([(ypub, my), (xpub, mx)])
-            crit, defer, _ = self.run_stage(K_TAIL, L, xin)
-            skpub = np.zeros((P, ms), np.float32)
-            for p in range(P):
-                c, r = divmod(p, CS)
-                bias = self.img[p]["b"]
-                h = crit[p, :ms].sum(axis=1) + bias[pl.bo_sb + (L - 1) * 4 * qS: pl.bo_sb + (L - 1) * 4 * qS + ms]
-                tot = h if L == 1 else skipacc[p] + h
-                s0, ns = own(S, NC, CS, c, r)
-                skpub[p, :ns] = np.maximum(tot * np.float32(math.sqrt(1.0 / L)), 0)[:ns]
-                for tap in range(kw - 1):
-                    D = (kw - 1 - tap) * dil[L - 1]
-                    rings[p][L - 1][tap][t % D] = defer[p, tap * 2 * my:(tap + 1) * 2 * my].sum(axis=1)
-            crit, _, _ = self.run_stage(K_HEAD1, L + 1, slices([(skpub, ms)]))
-            h1pub = np.zeros((P, ms), np.float32)
-            for p in range(P):
-                c, r = divmod(p, CS)
-                a0, na = own(S, NC, CS, c, r)
-                h1pub[p, :na] = np.maximum(crit[p, :ms].sum(axis=1) + self.img[p]["b"][pl.bo_ha:pl.bo_ha + ms], 0)[:na]
-            crit, _, _ = self.run_stage(K_HEAD2, L + 2, slices([(h1pub, ms)]))
-            for p in range(P):
-                c, r = divmod(p, CS)
-                b0, nb = own(O, NC, CS, c, r)
-                out[b0:b0 + nb, t] = (crit[p, :mo].sum(axis=1) + self.img[p]["b"][pl.bo_hb:pl.bo_hb + mo])[:nb]
+                        x_prev = x_new
+            h1 = np.zeros(S, np.float32)
+            for p, lst in enumerate(self.run_stage(K_HEAD1, L + 1, sk)):
+                a0, na = own[p]["a"]
+                for ps, v in lst:
+                    assert ps.job == J_HA
+                    for r in range(2):
+                        j = ps.idx + r
+                        if j < na:
+                            h1[a0 + j] = max(v[r] + self.img[p]["b"][pl.bo_ha + j], 0)
+            for p, lst in enumerate(self.run_stage(K_HEAD2, L + 2, h1)):
+                b0, nb = own[p]["b"]
+                for ps, v in lst:
+                    assert ps.job == J_HB
+                    for r in range(2):
+                        j = ps.idx + r
+                        if j < nb:
+                            out[b0 + j, t] = v[r] + self.img[p]["b"][pl.bo_hb + j]
         return out
 
 
-@pytest.mark.parametrize("name,P,cluster", [("mol_cond", 5, 0), ("mol_cond", 32, 8), ("mol_cond", 16, 4),
-                                            ("mulaw_softmax", 16, 0), ("gauss_speaker", 3, 0), ("mixgauss", 6, 2),
-                                            ("mol_upsample", 24, 0), ("mol_cond", 16, 16)])
-def test_packed_image_replays_reference(name, P, cluster):
+@pytest.mark.parametrize("name,P", [("mol_cond", 5), ("mol_cond", 16), ("mulaw_softmax", 16),
+                                    ("gauss_speaker", 3), ("mixgauss", 7), ("mol_upsample", 12)])
+def test_packed_image_replays_reference(name, P):
     gc = GoldenCase(name)
-    pm = PackedModel(gc, P, cluster)
-    if cluster:
-        assert pm.pl.CS == cluster
+    pm = PackedModel(gc, P)
     got = pm.run_teacher_forced(0)
     ref = gc.arr["params_tf"][0]
     assert got.shape == ref.shape
@@ -322,32 +302,27 @@ def test_packed_image_replays_reference(name, P, cluster):
 
 
 def test_pass_lists_cover_every_row_once():
-    """Every (owner, row slot) of every job receives exactly one tile per stage kind, critical passes precede
-    deferred ones in every warp, and tiles do not overlap inside a blob."""
+    """Every row pair of every job appears in exactly one pass per stage kind, critical passes precede deferred ones
+    in every warp, and tiles do not overlap inside a blob."""
     cfg = make_config(layers=24, stacks=4, residual_channels=512, gate_channels=512, skip_out_channels=256,
                       out_channels=30, kernel_size=3, cin_channels=80, gin_channels=-1, scalar_input=True,
                       output_distribution="Logistic")
     for batch in (1, 8):
         pl, passes = N.plan_passes(cfg, batch)
-        assert (pl.NC, pl.CS, pl.P, pl.BT) == (16, 8, 128, batch)
+        assert (pl.P, pl.BT, pl.my, pl.mx, pl.ms, pl.mo) == (128, batch, 2, 4, 2, 2)
+        want = {K_FIRST: {J_A0: [0, 1]}, K_LAYER: {J_A: [0, 1], J_B: [0, 2], J_D: [0, 1, 2, 3], J_S: [0]},
+                K_TAIL: {J_SL: [0], J_D: [0, 1, 2, 3]}, K_HEAD1: {J_HA: [0]}, K_HEAD2: {J_HB: [0]}}
         for kind in range(5):
             seen = {}
             spans = []
             for wv in range(8):
                 b0, n, nc = pl.pass_begin[kind][wv], pl.pass_count[kind][wv], pl.pass_crit[kind][wv]
                 for i, ps in enumerate(passes[b0:b0 + n]):
-                    assert (ps.dst != 1) == (i < nc)
-                    spans.append((ps.w_off, ps.w_off + ps.nit * 128))
-                    for g in range(2):
-                        if ps.owner[g] >= 0:
-                            key = (ps.dst, ps.owner[g], ps.dst_row[g])
-                            assert key not in seen
-                            seen[key] = ps.job
-            rows_c = {(o, r) for (d, o, r) in seen if d == 0}
-            rows_d = {(o, r) for (d, o, r) in seen if d == 1}
-            rows_x = {(o, r) for (d, o, r) in seen if d == 2}
-            assert len(rows_c) * 4 == pl.rows_c[kind] * pl.CS and len(rows_d) * 4 == pl.rows_d[kind] * pl.CS
-            assert len(rows_x) * 4 == (pl.rows_x * pl.CS if kind == K_LAYER else 0)
+                    assert (ps.deferred == 0) == (i < nc)
+                    assert ps.x_off % 4 == 0 and ps.x_off + 128 * ps.nit <= pl.xin_vals
+                    spans.append((ps.w_off, ps.w_off + ps.nit * 256))
+                    seen.setdefault(ps.job, []).append(ps.idx)
+            assert {j: sorted(v) for j, v in seen.items()} == want[kind]
             if kind in (K_FIRST, K_LAYER):
                 spans.sort()
                 assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libwn.so")
 SOURCES = [os.path.join(HERE, "csrc", "wn_host.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("wn_plan.h", "wn_kernel.cuh", "wn6_plan.h", "wn6_kernel.cuh",
-                                                     "wn6_host.cuh", "wn_aux.cuh")] + [os.path.join(ROOT, "include", "wn.h")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("wn_plan.h", "wn_kernel.cuh", "wn7_plan.h", "wn7_kernel.cuh",
+                                                     "wn7_host.cuh", "wn_aux.cuh")] + [os.path.join(ROOT, "include", "wn.h")]
 
 WN_ABI_VERSION = 2
 WN_INPUT_SCALAR, WN_INPUT_ONEHOT = 0, 1
@@ -32,7 +32,7 @@ class wn_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "layers", "stacks", "residual_channels", "gate_channels", "skip_channels",
         "out_channels", "kernel_size", "cin_channels", "gin_channels", "input_kind", "head_kind",
-        "device", "num_ctas", "exchange_copies", "ring_slots", "cluster_size")] + [("reserved", C.c_int32 * 7)]
+        "device", "num_ctas", "exchange_copies", "ring_slots", "poll_warps")] + [("reserved", C.c_int32 * 7)]
 
 
 class wn_layer_weights(C.Structure):
@@ -77,49 +77,47 @@ class wn_plan_info(C.Structure):
             "smem_bytes", "layer_blob_bytes", "head_blob_bytes", "packed_bytes_per_cta",
             "weight_bytes_per_step", "flops_per_sample", "streamed_bytes_per_step", "launches",
             "cond_packed_bytes_per_cta", "bias_packed_bytes_per_cta", "num_clusters", "cluster_size",
-            "num_passes", "engine")] + [("reserved", C.c_int64 * 1)]
+            "num_passes", "engine", "poll_warps")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
-class Wn6Pass(C.Structure):
-    """Mirror of struct Wn6Pass (csrc/wn6_plan.h): one warp pass = two row quads x nit k-steps."""
-    _fields_ = [("w_off", C.c_int32), ("nit", C.c_int16), ("x_off", C.c_int16), ("dst_row", C.c_int16 * 2),
-                ("owner", C.c_int8 * 2), ("dst", C.c_int8), ("job", C.c_int8), ("quad", C.c_int16 * 2)]
+class Wn7Pass(C.Structure):
+    """Mirror of struct Wn7Pass (csrc/wn7_plan.h): one warp pass = two complete rows x nit k-steps."""
+    _fields_ = [("w_off", C.c_int32), ("nit", C.c_int16), ("x_off", C.c_int16), ("idx", C.c_int16),
+                ("job", C.c_int8), ("deferred", C.c_int8)]
 
 
 _NKIND, _NCW = 5, 8
 
 
-class Wn6Plan(C.Structure):
-    """Mirror of struct Wn6Plan (csrc/wn6_plan.h); filled by wn_plan_passes."""
+class Wn7Plan(C.Structure):
+    """Mirror of struct Wn7Plan (csrc/wn7_plan.h); filled by wn_plan_passes."""
     _fields_ = ([(n, C.c_int32) for n in ("L", "per_stack", "R", "G", "G2", "S", "O", "kw", "C", "gin", "input_kind",
                                           "head_kind", "Kmix")] + [("skip_scale", C.c_float)] +
-                [(n, C.c_int32) for n in ("NC", "CS", "P", "BT", "my", "mx", "ms", "mo", "qA", "qB", "qD", "qS", "qHA",
-                                          "qHB", "Ky", "Kx", "Ksk", "Kh2", "xin_vals", "NS", "rs_yx", "rs_sk", "rs_h2")] +
-                [(n, C.c_int64) for n in ("ex_yx", "ex_sk", "ex_h1", "ex_h2", "ex_pairs")] +
-                [("nrow_c", C.c_int32), ("nrow_d", C.c_int32), ("nrow_x", C.c_int32), ("rows_c", C.c_int32 * _NKIND),
-                 ("rows_d", C.c_int32 * _NKIND), ("rows_x", C.c_int32), ("npass", C.c_int32),
+                [(n, C.c_int32) for n in ("P", "BT", "npw", "my", "mx", "ms", "mo", "xoff", "xin_vals", "NS")] +
+                [(n, C.c_int64) for n in ("slot_pairs", "ex_pairs")] +
+                [("npass", C.c_int32),
                  ("pass_begin", (C.c_int32 * _NCW) * _NKIND), ("pass_count", (C.c_int32 * _NCW) * _NKIND),
-                 ("pass_crit", (C.c_int32 * _NCW) * _NKIND)] +
+                 ("pass_crit", (C.c_int32 * _NCW) * _NKIND), ("has_deferred", C.c_int32 * _NKIND)] +
                 [(n, C.c_int32) for n in ("fb_floats", "lb_floats", "tb_floats", "slot_floats")] +
                 [("cta_w_floats", C.c_int64)] +
                 [(n, C.c_int32) for n in ("nblobs", "nres", "nring", "bo_zb", "bo_xb", "bo_sb", "bo_ha", "bo_hb",
-                                          "cta_b_floats")] +
+                                          "cta_b_floats", "qA")] +
                 [("cta_cw_floats", C.c_int64), ("ring_in_smem", C.c_int32), ("ring_pos_total", C.c_int64)] +
-                [(n, C.c_int32) for n in ("sm_bar", "sm_misc", "sm_pass", "sm_ringtab", "sm_xin", "sm_part", "sm_dpart", "sm_partx",
-                                          "sm_sb", "sm_pre", "sm_cond", "sm_bias", "sm_skipacc", "sm_xown", "sm_hs",
-                                          "sm_noise", "sm_in", "sm_x0w", "sm_ring", "sm_slots", "smem_bytes")])
+                [(n, C.c_int32) for n in ("sm_bar", "sm_misc", "sm_pass", "sm_ringtab", "sm_xin", "sm_sb", "sm_pre",
+                                          "sm_cond", "sm_bias", "sm_skipacc", "sm_xown", "sm_hs", "sm_noise", "sm_in",
+                                          "sm_x0w", "sm_ring", "sm_slots", "smem_bytes", "nthreads")])
 
 
 def plan_passes(cfg, batch=1, num_sms=148, smem=232448):
-    """(Wn6Plan, [Wn6Pass]) the planner of the cluster engine produces for `cfg` (no GPU needed)."""
-    pl = Wn6Plan()
+    """(Wn7Plan, [Wn7Pass]) the planner produces for `cfg` (no GPU needed)."""
+    pl = Wn7Plan()
     n = lib().wn_plan_passes(C.byref(cfg), batch, num_sms, smem, C.cast(C.byref(pl), _i32p), C.sizeof(pl) // 4, None, 0)
     if n < 0:
         check(n)
-    ps = (Wn6Pass * max(n, 1))()
+    ps = (Wn7Pass * max(n, 1))()
     n = lib().wn_plan_passes(C.byref(cfg), batch, num_sms, smem, C.cast(C.byref(pl), _i32p), C.sizeof(pl) // 4,
                              C.cast(ps, C.c_void_p), n)
     if n < 0:

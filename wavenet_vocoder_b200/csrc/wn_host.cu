@@ -14,8 +14,8 @@
 #include "../../include/wn.h"
 #include "wn_plan.h"
 #include "wn_kernel.cuh"
-#include "wn6_plan.h"
-#include "wn6_kernel.cuh"
+#include "wn7_plan.h"
+#include "wn7_kernel.cuh"
 #include "wn_aux.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -263,7 +263,6 @@ static void fill_info(const wn_config& c, const WnPlan& pl, wn_plan_info* out) {
     out->smem_bytes = pl.smem_bytes;
     out->layer_blob_bytes = (int64_t)pl.lb_floats * 4;
     out->head_blob_bytes = (int64_t)pl.tb_floats * 4;
-    out->reserved[0] = (int64_t)pl.fb_floats * 4;   // first-blob bytes
     out->packed_bytes_per_cta = (int64_t)pl.cta_w_floats * 4;
     out->cond_packed_bytes_per_cta = (int64_t)pl.cta_cw_floats * 4;
     const int64_t cin0 = (c.input_kind == WN_INPUT_SCALAR) ? 1 : pl.O;
@@ -422,24 +421,22 @@ static int32_t check_weights(const wn_config& c, const wn_weights* w) {
     return WN_OK;
 }
 
-#include "wn6_host.cuh"
+#include "wn7_host.cuh"
 
-// which kernel generation: 6 = thread-block clusters + DSMEM (default), 5 = the round-1 all-poll kernel
-static int engine_choice() { return env_int("WN_ENGINE", 6) == 5 ? 5 : 6; }
+// which kernel generation: 7 = polling warps + warp-per-row-pair passes (default), 5 = the round-1 kernel
+static int engine_choice() { return env_int("WN_ENGINE", 7) == 5 ? 5 : 7; }
 
 // ------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------
 struct WnHandle {
     wn_config cfg;
-    int engine = 6;
-    Wn6Plan base6;                // plan for BT=1 (grid, passes and blob layout are batch independent)
-    std::vector<Wn6Pass> passes6;
+    int engine = 7;
+    Wn7Plan base7;                // plan for BT=1 (grid, passes and blob layout are batch independent)
+    std::vector<Wn7Pass> passes7;
     float* d_bpack = nullptr;
-    Wn6Pass* d_passes = nullptr;
-    int max_clusters = 0;
-    bool attr6_set[4] = {};
-    bool coop_with_clusters = true;
+    Wn7Pass* d_passes = nullptr;
+    bool attr7_set[4] = {};
     // local-conditioning upsampler (wn_load_upsampler)
     bool have_ups = false;
     wnaux::UpsampleDesc ups;
@@ -480,7 +477,7 @@ static int32_t ensure(T** ptr, size_t* have, size_t need) {
     return WN_OK;
 }
 
-static int max_tile(int engine) { return std::max(1, std::min(8, env_int("WN_MAX_TILE", engine == 6 ? 8 : 4))); }
+static int max_tile(int engine) { return std::max(1, std::min(8, env_int("WN_MAX_TILE", engine == 7 ? 8 : 4))); }
 static int bt_index(int BT) { return BT == 1 ? 0 : BT == 2 ? 1 : BT == 4 ? 2 : 3; }
 
 static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
@@ -612,10 +609,10 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     return WN_OK;
 }
 
-static void fill_info6(const wn_config& c, const Wn6Plan& pl, wn_plan_info* out) {
+static void fill_info7(const wn_config& c, const Wn7Plan& pl, wn_plan_info* out) {
     memset(out, 0, sizeof(*out));
     out->num_ctas = pl.P;
-    out->threads_per_cta = WN6_NTHREADS;
+    out->threads_per_cta = pl.nthreads;
     out->batch_tile = pl.BT;
     out->rows_y = pl.my;
     out->rows_x = pl.mx;
@@ -634,10 +631,11 @@ static void fill_info6(const wn_config& c, const Wn6Plan& pl, wn_plan_info* out)
     out->packed_bytes_per_cta = (int64_t)pl.cta_w_floats * 4;
     out->cond_packed_bytes_per_cta = (int64_t)pl.cta_cw_floats * 4;
     out->bias_packed_bytes_per_cta = (int64_t)pl.cta_b_floats * 4;
-    out->num_clusters = pl.NC;
-    out->cluster_size = pl.CS;
+    out->num_clusters = pl.P;
+    out->cluster_size = 1;
+    out->poll_warps = pl.npw;
     out->num_passes = pl.npass;
-    out->engine = 6;
+    out->engine = 7;
     const int64_t cin0 = (c.input_kind == WN_INPUT_SCALAR) ? 1 : pl.O;
     // MAC = C0*R + L*(G*kw*R + G*C + S*G/2 + R*G/2) + S*S + O*S ; weights = MAC + biases
     const int64_t mac = cin0 * pl.R + (int64_t)pl.L * ((int64_t)pl.G * pl.kw * pl.R + (int64_t)pl.G * pl.C +
@@ -647,7 +645,7 @@ static void fill_info6(const wn_config& c, const Wn6Plan& pl, wn_plan_info* out)
     out->flops_per_sample = 2 * mac;
     out->weight_bytes_per_step = 4 * (mac + biases);
     int64_t streamed = 0;
-    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += wn6_blob_floats(pl, i) * 4LL;
+    for (int i = pl.nres; i < pl.nblobs; ++i) streamed += wn7_blob_floats(pl, i) * 4LL;
     out->streamed_bytes_per_step = streamed * pl.P;
 }
 
@@ -678,32 +676,31 @@ static int32_t run_upsampler(WnHandle* h, const float* c_frames, int B, int F, i
     return WN_OK;
 }
 
-static const void* kernel6_for(int BT) {
+static const void* kernel7_for(int BT) {
     switch (BT) {
-        case 1: return (const void*)wn6::wn6_kernel<1>;
-        case 2: return (const void*)wn6::wn6_kernel<2>;
-        case 4: return (const void*)wn6::wn6_kernel<4>;
-        default: return (const void*)wn6::wn6_kernel<8>;
+        case 1: return (const void*)wn7::wn7_kernel<1>;
+        case 2: return (const void*)wn7::wn7_kernel<2>;
+        case 4: return (const void*)wn7::wn7_kernel<4>;
+        default: return (const void*)wn7::wn7_kernel<8>;
     }
 }
 
-static int32_t prepare_kernel6(WnHandle* h, int BT, int CS) {
+static int32_t prepare_kernel7(WnHandle* h, int BT) {
     const int ai = bt_index(BT);
-    if (h->attr6_set[ai]) return WN_OK;
-    const void* fn = kernel6_for(BT);
+    if (h->attr7_set[ai]) return WN_OK;
+    const void* fn = kernel7_for(BT);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
-    if (CS > 8) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    h->attr6_set[ai] = true;
+    h->attr7_set[ai] = true;
     return WN_OK;
 }
 
-static int32_t launch_chunk6(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
-    Wn6Plan pl;
-    std::vector<Wn6Pass> passes;
+static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int Bc, cudaStream_t st) {
+    Wn7Plan pl;
+    std::vector<Wn7Pass> passes;
     std::vector<int> rt;
-    int32_t rc = build_plan6(h->cfg, Bc, h->num_sms, h->smem_cap, h->max_clusters, pl, passes, rt);
+    int32_t rc = build_plan7(h->cfg, Bc, h->num_sms, h->smem_cap, pl, passes, rt);
     if (rc) return rc;
-    if (pl.P != h->base6.P || pl.CS != h->base6.CS || pl.lb_floats != h->base6.lb_floats || pl.npass != h->base6.npass)
+    if (pl.P != h->base7.P || pl.lb_floats != h->base7.lb_floats || pl.npass != h->base7.npass)
         return fail(WN_ERR_STATE, "plan changed between weight upload and generate");
     const int BT = pl.BT;
     const wn_config& c = h->cfg;
@@ -717,14 +714,14 @@ static int32_t launch_chunk6(WnHandle* h, const wn_generate_args* a, int b0, int
         if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(h->d_ring, 0, rb, st));
     }
-    Wn6Ptrs pp;
+    Wn7Ptrs pp;
     memset(&pp, 0, sizeof(pp));
     if (c.gin_channels > 0) {
         if (!a->g) return fail(WN_ERR_INVALID, "g is required (gin_channels > 0), cf. train.py:72-80 sanity_check");
         const size_t gb = (size_t)Bc * pl.L * pl.G * sizeof(float);
         rc = ensure(&h->d_gbias, &h->gbias_bytes, gb);
         if (rc) return rc;
-        wn6::wn6_gbias_kernel<<<dim3(pl.L, Bc), 128, 0, st>>>(h->d_wg, a->g + (size_t)b0 * c.gin_channels, h->d_gbias,
+        wn7::wn7_gbias_kernel<<<dim3(pl.L, Bc), 128, 0, st>>>(h->d_wg, a->g + (size_t)b0 * c.gin_channels, h->d_gbias,
                                                             pl.L, pl.G, c.gin_channels);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -775,42 +772,23 @@ static int32_t launch_chunk6(WnHandle* h, const wn_generate_args* a, int b0, int
         CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, pb, st));
         pp.prof = h->d_prof;
     }
-    rc = prepare_kernel6(h, BT, pl.CS);
+    rc = prepare_kernel7(h, BT);
     if (rc) return rc;
     void* kargs[2] = {(void*)&pl, (void*)&pp};
+    // cooperative launch: the runtime refuses to start unless all P blocks are co-resident, which the
+    // spin-wait exchanges require
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3(pl.P);
-    lc.blockDim = dim3(WN6_NTHREADS);
+    lc.blockDim = dim3(pl.nthreads);
     lc.dynamicSmemBytes = (size_t)pl.smem_bytes;
     lc.stream = st;
-    cudaLaunchAttribute la[2];
-    int na = 0;
-    la[na].id = cudaLaunchAttributeClusterDimension;
-    la[na].val.clusterDim.x = (unsigned)pl.CS;
-    la[na].val.clusterDim.y = 1;
-    la[na].val.clusterDim.z = 1;
-    ++na;
-    // cooperative launch: the runtime refuses to start unless all blocks are co-resident, which the
-    // spin-wait exchanges require
-    if (h->coop_with_clusters) {
-        la[na].id = cudaLaunchAttributeCooperative;
-        la[na].val.cooperative = 1;
-        ++na;
-    }
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeCooperative;
+    la[0].val.cooperative = 1;
     lc.attrs = la;
-    lc.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs);
-    if (le != cudaSuccess && h->coop_with_clusters) {
-        // some driver / runtime combinations refuse the cooperative attribute together with a cluster dimension:
-        // fall back to a plain cluster launch (the grid never exceeds the co-resident cluster count the occupancy
-        // query reported at wn_create, so the blocks are co-resident on an otherwise idle GPU)
-        cudaGetLastError();
-        lc.numAttrs = 1;
-        le = cudaLaunchKernelExC(&lc, kernel6_for(BT), kargs);
-        if (le == cudaSuccess) h->coop_with_clusters = false;
-    }
-    if (le != cudaSuccess) return fail(WN_ERR_CUDA, std::string("cudaLaunchKernelExC: ") + cudaGetErrorString(le));
+    lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelExC(&lc, kernel7_for(BT), kargs));
     h->launches++;
     return WN_OK;
 }
@@ -825,13 +803,13 @@ const char* wn_last_error(void) { return g_err.c_str(); }
 
 int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, wn_plan_info* out) {
     if (!cfg || !out) return fail(WN_ERR_INVALID, "null argument");
-    if (engine_choice() == 6) {
-        Wn6Plan pl6;
-        std::vector<Wn6Pass> ps;
+    if (engine_choice() == 7) {
+        Wn7Plan pl6;
+        std::vector<Wn7Pass> ps;
         std::vector<int> rt6;
-        int32_t rc6 = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl6, ps, rt6);
+        int32_t rc6 = build_plan7(*cfg, batch, num_sms, smem_per_cta, pl6, ps, rt6);
         if (rc6) return rc6;
-        fill_info6(*cfg, pl6, out);
+        fill_info7(*cfg, pl6, out);
         return WN_OK;
     }
     WnPlan pl;
@@ -845,18 +823,18 @@ int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64
 int32_t wn_plan_passes(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, int32_t* plan_words,
                        int32_t max_plan_words, void* passes, int32_t max_passes) {
     if (!cfg) return fail(WN_ERR_INVALID, "null argument");
-    Wn6Plan pl;
-    std::vector<Wn6Pass> ps;
+    Wn7Plan pl;
+    std::vector<Wn7Pass> ps;
     std::vector<int> rt;
-    int32_t rc = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl, ps, rt);
+    int32_t rc = build_plan7(*cfg, batch, num_sms, smem_per_cta, pl, ps, rt);
     if (rc) return rc;
     if (plan_words) {
-        const int n = std::min<int>(max_plan_words, (int)(sizeof(Wn6Plan) / 4));
+        const int n = std::min<int>(max_plan_words, (int)(sizeof(Wn7Plan) / 4));
         memcpy(plan_words, &pl, (size_t)n * 4);
     }
     if (passes) {
         if (max_passes < pl.npass) return fail(WN_ERR_INVALID, "pass buffer too small");
-        memcpy(passes, ps.data(), ps.size() * sizeof(Wn6Pass));
+        memcpy(passes, ps.data(), ps.size() * sizeof(Wn7Pass));
     }
     return pl.npass;
 }
@@ -864,11 +842,11 @@ int32_t wn_plan_passes(const wn_config* cfg, int32_t batch, int32_t num_sms, int
 int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, const wn_weights* w,
                     int32_t cta, float* packed, int64_t packed_floats) {
     if (!cfg || !packed) return fail(WN_ERR_INVALID, "null argument");
-    if (engine_choice() == 6) {
-        Wn6Plan pl6;
-        std::vector<Wn6Pass> ps;
+    if (engine_choice() == 7) {
+        Wn7Plan pl6;
+        std::vector<Wn7Pass> ps;
         std::vector<int> rt6;
-        int32_t rc6 = build_plan6(*cfg, batch, num_sms, smem_per_cta, 0, pl6, ps, rt6);
+        int32_t rc6 = build_plan7(*cfg, batch, num_sms, smem_per_cta, pl6, ps, rt6);
         if (rc6) return rc6;
         rc6 = check_weights(*cfg, w);
         if (rc6) return rc6;
@@ -876,12 +854,12 @@ int32_t wn_pack_cta(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_
         if (packed_floats < pl6.cta_w_floats) return fail(WN_ERR_INVALID, "packed buffer too small");
         Folded fo;
         fold_layers(pl6.L, pl6.G, pl6.R, pl6.G2, pl6.kw, *w, fo);
-        pack6_cta(pl6, ps, *w, fo, cta, packed);
+        pack7_cta(pl6, ps, *w, fo, cta, packed);
         long long off = pl6.cta_w_floats;
         if (packed_floats >= off + pl6.cta_cw_floats) {
-            pack6_cw(pl6, *w, cta, packed + off);
+            pack7_cw(pl6, *w, cta, packed + off);
             off += pl6.cta_cw_floats;
-            if (packed_floats >= off + pl6.cta_b_floats) pack6_bias(pl6, *w, fo, cta, packed + off);
+            if (packed_floats >= off + pl6.cta_b_floats) pack7_bias(pl6, *w, fo, cta, packed + off);
         }
         return WN_OK;
     }
@@ -924,35 +902,8 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
     h->num_sms = prop.multiProcessorCount;
     h->smem_cap = (long long)prop.sharedMemPerBlockOptin;
     int32_t rc;
-    if (h->engine == 6) {
-        // first plan with the default cluster budget, then ask the runtime how many clusters really fit
-        rc = build_plan6(h->cfg, 1, h->num_sms, h->smem_cap, 0, h->base6, h->passes6, h->ringtab);
-        if (rc == WN_OK && h->cfg.num_ctas <= 0 && env_int("WN_NUM_CTAS", 0) <= 0) {
-            const int CS = h->base6.CS;
-            if (prepare_kernel6(h, 1, CS) == WN_OK) {
-                cudaLaunchConfig_t lc;
-                memset(&lc, 0, sizeof(lc));
-                lc.gridDim = dim3(h->base6.P);
-                lc.blockDim = dim3(WN6_NTHREADS);
-                lc.dynamicSmemBytes = (size_t)h->smem_cap;
-                cudaLaunchAttribute la[1];
-                la[0].id = cudaLaunchAttributeClusterDimension;
-                la[0].val.clusterDim.x = (unsigned)CS;
-                la[0].val.clusterDim.y = 1;
-                la[0].val.clusterDim.z = 1;
-                lc.attrs = la;
-                lc.numAttrs = 1;
-                int ncl = 0;
-                if (cudaOccupancyMaxActiveClusters(&ncl, kernel6_for(1), &lc) == cudaSuccess && ncl > 0) {
-                    h->max_clusters = ncl;
-                    if (ncl < h->base6.NC)
-                        rc = build_plan6(h->cfg, 1, h->num_sms, h->smem_cap, ncl, h->base6, h->passes6, h->ringtab);
-                } else {
-                    cudaGetLastError();
-                }
-            }
-        }
-        h->coop_with_clusters = env_int("WN_COOP", 1) != 0;
+    if (h->engine == 7) {
+        rc = build_plan7(h->cfg, 1, h->num_sms, h->smem_cap, h->base7, h->passes7, h->ringtab);
     } else {
         rc = build_plan(h->cfg, 1, h->num_sms, h->smem_cap, h->base, h->ringtab);
     }
@@ -971,9 +922,9 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
         }
     }
     // freeze the partition so every batch tile agrees with the packing
-    if (h->engine == 6) {
-        h->cfg.num_ctas = h->base6.P;
-        h->cfg.cluster_size = h->base6.CS;
+    if (h->engine == 7) {
+        h->cfg.num_ctas = h->base7.P;
+        h->cfg.poll_warps = h->base7.npw;
     } else {
         h->cfg.num_ctas = h->base.P;
         h->cfg.exchange_copies = h->base.ncopy;
@@ -1016,17 +967,17 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
         return WN_OK;
     };
     struct Shape { int L, G, R, G2, kw, O, P; } pl;
-    if (h->engine == 6) {
-        const Wn6Plan& p6 = h->base6;
+    if (h->engine == 7) {
+        const Wn7Plan& p6 = h->base7;
         pl = {p6.L, p6.G, p6.R, p6.G2, p6.kw, p6.O, p6.P};
         Folded fo;
         fold_layers(pl.L, pl.G, pl.R, pl.G2, pl.kw, *w, fo);
         std::vector<float> img((size_t)p6.P * p6.cta_w_floats), cw((size_t)p6.P * p6.cta_cw_floats),
             bs((size_t)p6.P * p6.cta_b_floats);
         for (int p = 0; p < p6.P; ++p) {
-            pack6_cta(p6, h->passes6, *w, fo, p, img.data() + (size_t)p * p6.cta_w_floats);
-            pack6_cw(p6, *w, p, cw.data() + (size_t)p * p6.cta_cw_floats);
-            pack6_bias(p6, *w, fo, p, bs.data() + (size_t)p * p6.cta_b_floats);
+            pack7_cta(p6, h->passes7, *w, fo, p, img.data() + (size_t)p * p6.cta_w_floats);
+            pack7_cw(p6, *w, p, cw.data() + (size_t)p * p6.cta_cw_floats);
+            pack7_bias(p6, *w, fo, p, bs.data() + (size_t)p * p6.cta_b_floats);
         }
         if ((rc = upload(&h->d_wpack, img))) return rc;
         h->wpack_bytes = img.size() * sizeof(float);
@@ -1034,8 +985,8 @@ int32_t wn_load_weights(void* handle, const wn_weights* w) {
         if ((rc = upload(&h->d_bpack, bs))) return rc;
         if (h->d_passes) cudaFree(h->d_passes);
         h->d_passes = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&h->d_passes, std::max<size_t>(16, h->passes6.size() * sizeof(Wn6Pass))));
-        CUDA_TRY(cudaMemcpy(h->d_passes, h->passes6.data(), h->passes6.size() * sizeof(Wn6Pass), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void**)&h->d_passes, std::max<size_t>(16, h->passes7.size() * sizeof(Wn7Pass))));
+        CUDA_TRY(cudaMemcpy(h->d_passes, h->passes7.data(), h->passes7.size() * sizeof(Wn7Pass), cudaMemcpyHostToDevice));
     } else {
         const WnPlan& p5 = h->base;
         pl = {p5.L, p5.G, p5.R, p5.G2, p5.kw, p5.O, p5.P};
@@ -1109,8 +1060,8 @@ static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
         const int start = a->initial_index < 0 ? 127 : a->initial_index;
         if (a->T_test == 0 && !a->initial_rows && !a->initial_dense && start >= c.out_channels)
             return fail(WN_ERR_INVALID, "initial_index out of range (the default start class is 127, wavenet.py:286)");
-        if ((a->initial_rows || a->initial_dense) && h->engine != 6)
-            return fail(WN_ERR_INVALID, "per-utterance initial inputs need the cluster engine");
+        if ((a->initial_rows || a->initial_dense) && h->engine != 7)
+            return fail(WN_ERR_INVALID, "per-utterance initial inputs need the default engine");
     }
     if (a->noise_kind == WN_NOISE_REPLAY) {
         const bool quant = (a->flags & WN_FLAG_QUANTIZE) != 0;
@@ -1144,7 +1095,7 @@ int32_t wn_generate(void* handle, const wn_generate_args* a) {
     const int tile = max_tile(h->engine);
     for (int b0 = 0; b0 < a->B; b0 += tile) {
         const int Bc = std::min(tile, a->B - b0);
-        rc = h->engine == 6 ? launch_chunk6(h, a, b0, Bc, st) : launch_chunk(h, a, b0, Bc, st);
+        rc = h->engine == 7 ? launch_chunk7(h, a, b0, Bc, st) : launch_chunk(h, a, b0, Bc, st);
         if (rc) return rc;
     }
     h->last_stream = st;
@@ -1166,10 +1117,10 @@ int32_t wn_sync(void* handle) {
         const char* names5[16] = {"C.poll", "C.gemv", "C.barrier", "C.finalize+publish", "C.acquire+pre", "C.head",
                                   "C.sample+sync", "C.x0", "D.wait_stash", "D.gemv", "D.finalize", "D.sample+sync",
                                   "-", "-", "-", "-"};
-        const char* names6[16] = {"F0.wait_partials", "F0.finalise+publish", "-", "-", "-", "-", "-", "-",
-                                  "W0.acquire_blob", "W0.wait_input", "W0.critical_passes", "W0.deferred+release",
+        const char* names7[16] = {"-", "-", "-", "-", "-", "-", "-", "-",
+                                  "W0.acquire_blob+pre", "W0.wait_input", "W0.critical_passes", "W0.deferred+release",
                                   "-", "-", "-", "-"};
-        const char** names = h->engine == 6 ? names6 : names5;
+        const char** names = h->engine == 7 ? names7 : names5;
         const int P = (int)(pc.size() / 16);
         for (int i = 0; i < 12; ++i) {
             long long mn = pc[i], mx = pc[i], sum = 0;
@@ -1191,13 +1142,13 @@ int32_t wn_get_plan(void* handle, int32_t batch, wn_plan_info* out) {
     WnHandle* h = (WnHandle*)handle;
     if (!h || !out) return fail(WN_ERR_INVALID, "null argument");
     const int bt = std::min(std::max(batch, 1), max_tile(h->engine));
-    if (h->engine == 6) {
-        Wn6Plan pl6;
-        std::vector<Wn6Pass> ps;
+    if (h->engine == 7) {
+        Wn7Plan pl6;
+        std::vector<Wn7Pass> ps;
         std::vector<int> rt6;
-        int32_t rc6 = build_plan6(h->cfg, bt, h->num_sms, h->smem_cap, h->max_clusters, pl6, ps, rt6);
+        int32_t rc6 = build_plan7(h->cfg, bt, h->num_sms, h->smem_cap, pl6, ps, rt6);
         if (rc6) return rc6;
-        fill_info6(h->cfg, pl6, out);
+        fill_info7(h->cfg, pl6, out);
         out->launches = h->launches;
         return WN_OK;
     }
