@@ -569,8 +569,8 @@ def test_config2_width_batch_tiles_against_oracle(B):
 
 @pytest.mark.parametrize("B", [1, 4])
 def test_wide_stack_several_quads_per_owner(B):
-    """R = 768, G/2 = 384: every block owns 3 gate pairs / 6 residual rows -> two row quads per job and owner, with
-    padding rows inside the quads (the widest layer whose per-block blob still double-buffers in shared memory)."""
+    """R = 768, G/2 = 384: every block owns 3 gate pairs / 6 residual rows / 9-step tiles (a wide layer whose per-block
+    blob still double-buffers in shared memory)."""
     from wavenet_vocoder_b200 import WaveNet
     kw = dict(out_channels=30, layers=4, stacks=2, residual_channels=768, gate_channels=768, skip_out_channels=256,
               cin_channels=80, gin_channels=-1, scalar_input=True, output_distribution="Logistic", dropout=0.0)

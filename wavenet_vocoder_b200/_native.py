@@ -98,6 +98,7 @@ class Wn7Plan(C.Structure):
                                           "head_kind", "Kmix")] + [("skip_scale", C.c_float)] +
                 [(n, C.c_int32) for n in ("P", "BT", "npw", "my", "mx", "ms", "mo", "xoff", "xin_vals", "NS")] +
                 [(n, C.c_int64) for n in ("slot_pairs", "ex_pairs")] +
+                [(n, C.c_int32) for n in ("ex_a", "ex_b", "gate_cycles", "backoff_ns")] +
                 [("npass", C.c_int32),
                  ("pass_begin", (C.c_int32 * _NCW) * _NKIND), ("pass_count", (C.c_int32 * _NCW) * _NKIND),
                  ("pass_crit", (C.c_int32 * _NCW) * _NKIND), ("has_deferred", C.c_int32 * _NKIND)] +

@@ -159,8 +159,19 @@ static int32_t build_plan7(const wn_config& c, int batch, int num_sms, long long
     pl.cta_b_floats = align_up7(bo, 4);
 
     // ---- exchange map (pairs): one slot per stage, vector order == xin order, slots on 256-byte boundaries
-    pl.slot_pairs = align_up7((long long)std::max(std::max(xoff + R, S), pl.O) * BT + 2, 32);
-    pl.ex_pairs = (long long)pl.NS * pl.slot_pairs + 32;
+    {
+        // WN_EX_SPREAD: 0 contiguous; 1 (default) = 4 pairs (one 32-byte sector) per 256-byte granule; 3 = 8 pairs
+        // (64 bytes) per granule.  Measured (profiles/r2_xbench_v7*.txt): a contiguous vector sits on a handful of L2
+        // slices and its 128 x npw*32 polling lanes queue there (8446 vs 3836 cycles per stage in the skeleton).
+        const int sp = env_int("WN_EX_SPREAD", 1);
+        pl.ex_a = sp == 1 ? 2 : (sp == 3 ? 3 : (sp == 2 ? 1 : 0));
+        pl.ex_b = sp == 0 ? 0 : (sp == 2 ? 4 : 5);
+        const long long linear = (long long)std::max(std::max(xoff + R, S), pl.O) * BT + 2;
+        pl.slot_pairs = align_up7((((linear >> pl.ex_a) + 1) << pl.ex_b) + 32, 32);
+        pl.ex_pairs = (long long)pl.NS * pl.slot_pairs + 32;
+        pl.gate_cycles = env_int("WN_GATE_CYCLES", 0);
+        pl.backoff_ns = env_int("WN_BACKOFF_NS", 0);
+    }
 
     // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later; one position = 4qA*BT floats
     ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);

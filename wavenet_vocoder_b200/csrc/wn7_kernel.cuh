@@ -316,11 +316,15 @@ struct Engine {
     // barrier over the polling warps with a watchdog (a plain bar.sync would hang if one of them aborted)
     uint32_t ps_par = 0;
     __device__ __forceinline__ void poller_sync() {
-        if (!dead) mbar_arrive(bar_ps);
+        __syncwarp();
+        if (!dead && lane == 0) mbar_arrive(bar_ps);          // one arrival per polling warp
         wait_bar(bar_ps, ps_par, 0x00200000u);
         ps_par ^= 1u;
     }
-    __device__ __forceinline__ void publish(long long pair, float v, uint32_t tag) { st_pair(pp.xbuf + pair, v, tag); }
+    // `slot` = pair offset of the stage slot, `i` = linear pair index inside it
+    __device__ __forceinline__ void publish(long long slot, long long i, float v, uint32_t tag) {
+        st_pair(pp.xbuf + slot + wn7_phys(pl, i), v, tag);
+    }
 
     // ======================================================================================
     // weight streaming warp
@@ -608,7 +612,7 @@ struct Engine {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + u * NPL;
-                    if (j < nld) q[u] = ld_pair2(src + p0 + 2 * j);
+                    if (j < nld) q[u] = ld_pair2(src + wn7_phys(pl, p0 + 2 * j));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -616,6 +620,7 @@ struct Engine {
                     if (j < nld) bad |= (q[u].y ^ tag) | ((2 * j + 1 < npairs) ? (q[u].w ^ tag) : 0u);
                 }
                 if (bad == 0) break;
+                if (pl.backoff_ns > 0) __nanosleep(pl.backoff_ns);
                 if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                     dead = true;
                     break;
@@ -679,8 +684,9 @@ struct Engine {
             uint32_t spins = 0;
             long long t0 = 0;
             while (true) {
-                q = ld_pair2(src + 2 * j);
+                q = ld_pair2(src + wn7_phys(pl, 2 * j));
                 if (q.y == tag && (!two || q.w == tag)) break;
+                if (pl.backoff_ns > 0) __nanosleep(pl.backoff_ns);
                 if (((++spins) & 63u) == 0 && check_abort(tag, t0)) {
                     dead = true;
                     break;
@@ -716,6 +722,7 @@ struct Engine {
         const int pl_ = warp * 32 + lane, NS = pl.NS, L = pl.L, T = pp.T;
         const int xin_floats = pl.xin_vals * BT;
         uint32_t n = 0;
+        long long t_prev = clock64();
         for (int t = 0; t < T && !dead; ++t) {
             for (int s = 0; s < NS; ++s, ++n) {
                 const int par = n & 1;
@@ -723,11 +730,15 @@ struct Engine {
                     if (!wait_bar(&bar_free[par], ((n >> 1) - 1) & 1u, 0x10000000u | (uint32_t)s)) break;
                 }
                 float* xb = xin + (size_t)par * xin_floats;
+                // gate: the next vector cannot be complete earlier than the local chain + one L2 hop after this one, and
+                // polling earlier only loads the L2 slices the publishers are writing to
+                if (pl.gate_cycles > 0) { while (clock64() - t_prev < pl.gate_cycles) {} }
                 if (s == 0) {
                     if (t > 0) read_head_and_sample(t - 1, pl_, NPL);
                     if (dead) break;
                     write_x0(xb, pl_, NPL, true);
-                    mbar_arrive(bar_x0);          // x_0 at the rows this block owns is in place (read in stage 1)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_x0);     // x_0 at the rows this block owns is in place (read in stage 1)
                 } else {
                     const uint2* src = pp.xbuf + wn7_ex_off(pl, s - 1);
                     if (s <= L) {
@@ -740,7 +751,9 @@ struct Engine {
                     }
                     if (dead) break;
                 }
-                mbar_arrive(&bar_in[par]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_in[par]);     // one arrival per polling warp
+                t_prev = clock64();
             }
         }
         if (!dead) read_head_and_sample(T - 1, pl_, NPL);
@@ -832,7 +845,7 @@ struct Engine {
                 if (r != 0 || idx >= ny) break;
                 const float a = mine + pre[((size_t)s * RA4 + 2 * idx) * BT + b];
                 const float g = other + pre[((size_t)s * RA4 + 2 * idx + 1) * BT + b];
-                publish(ex + (long long)(y0 + idx) * BT + b, gate(a, g), tag);
+                publish(ex, (long long)(y0 + idx) * BT + b, gate(a, g), tag);
             } break;
             case WN7_J_B: {
                 // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
@@ -841,7 +854,7 @@ struct Engine {
                 const float o = mine + bias[pl.bo_xb + s * pl.mx + j];
                 const float xp = (s == 1) ? x0own[j * BT + b] : xown[j * BT + b];
                 const float xn = (o + xp) * RSQRT2;
-                publish(ex + (long long)(pl.xoff + x0r + j) * BT + b, xn, tag);
+                publish(ex, (long long)(pl.xoff + x0r + j) * BT + b, xn, tag);
                 xown[j * BT + b] = xn;
             } break;
             case WN7_J_D: {
@@ -863,17 +876,17 @@ struct Engine {
                 if (j >= ns) break;
                 float tot = mine + bias[pl.bo_sb + (pl.L - 1) * pl.ms + j];
                 if (pl.L >= 2) tot = skipacc[j * BT + b] + tot;
-                publish(ex + (long long)(s0 + j) * BT + b, fmaxf(tot * pl.skip_scale, 0.f), tag);
+                publish(ex, (long long)(s0 + j) * BT + b, fmaxf(tot * pl.skip_scale, 0.f), tag);
             } break;
             case WN7_J_HA: {
                 const int j = idx + r;
                 if (j >= na) break;
-                publish(ex + (long long)(a0 + j) * BT + b, fmaxf(mine + bias[pl.bo_ha + j], 0.f), tag);
+                publish(ex, (long long)(a0 + j) * BT + b, fmaxf(mine + bias[pl.bo_ha + j], 0.f), tag);
             } break;
             default: {   // WN7_J_HB
                 const int j = idx + r;
                 if (j >= nb) break;
-                publish(ex + (long long)(b0 + j) * BT + b, mine + bias[pl.bo_hb + j], tag);
+                publish(ex, (long long)(b0 + j) * BT + b, mine + bias[pl.bo_hb + j], tag);
             } break;
         }
         (void)t;
@@ -1002,12 +1015,12 @@ wn7_kernel(const __grid_constant__ Wn7Plan pl, const __grid_constant__ Wn7Ptrs p
         for (int i = 0; i < 2; ++i) {
             mbar_init(&eng.bar_cfull[i], 1);
             mbar_init(&eng.bar_cempty[i], 1);
-            mbar_init(&eng.bar_in[i], 32 * pl.npw);
+            mbar_init(&eng.bar_in[i], pl.npw);
             mbar_init(&eng.bar_free[i], WN7_NCW);
         }
         mbar_init(eng.bar_pre, 1);
-        mbar_init(eng.bar_x0, 32 * pl.npw);
-        mbar_init(eng.bar_ps, 32 * pl.npw);
+        mbar_init(eng.bar_x0, pl.npw);
+        mbar_init(eng.bar_ps, pl.npw);
         mbar_init(eng.bar_dstep, WN7_NCW);
         *eng.s_abort = 0;
         *eng.s_skipcnt = 0;

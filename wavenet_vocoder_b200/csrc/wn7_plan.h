@@ -67,6 +67,10 @@ struct Wn7Plan {
     int NS;                     // stages per step = L+3
     long long slot_pairs;       // pairs reserved per stage slot
     long long ex_pairs;
+    int ex_a, ex_b;             // physical pair index = ((i >> ex_a) << ex_b) + (i & (2^ex_a - 1)): 2^ex_a pairs per
+                                // 2^ex_b-pair granule, so that a stage's sectors spread over many L2 slices
+    int gate_cycles;            // pollers do not touch a vector earlier than this many cycles after the previous one
+    int backoff_ns;             // pause between two polling attempts of a lane
     // ---- pass lists: pass_begin[kind][warp] .. +pass_count, the first pass_crit of them critical
     int npass;
     int pass_begin[WN7_NKIND][WN7_NCW], pass_count[WN7_NKIND][WN7_NCW], pass_crit[WN7_NKIND][WN7_NCW];
@@ -107,8 +111,11 @@ WN_HD long long wn7_blob_off(const Wn7Plan& pl, int i) {
 WN_HD int wn7_blob_floats(const Wn7Plan& pl, int i) {
     return i == 0 ? pl.fb_floats : (i < pl.L ? pl.lb_floats : pl.tb_floats);
 }
-// pair offset of the exchange slot stage s publishes into
+// pair offset of the exchange slot stage s publishes into, and the physical position of pair i inside a slot
 WN_HD long long wn7_ex_off(const Wn7Plan& pl, int s) { return (long long)s * pl.slot_pairs; }
+WN_HD long long wn7_phys(const Wn7Plan& pl, long long i) {
+    return ((i >> pl.ex_a) << pl.ex_b) + (i & ((1LL << pl.ex_a) - 1));
+}
 // warp roles: [0,npw) pollers, [npw, npw+NCW) compute, then HK (pre-sums / ring positions), TMA, COND
 WN_HD int wn7_warp_comp(const Wn7Plan& pl) { return pl.npw; }
 WN_HD int wn7_warp_hk(const Wn7Plan& pl) { return pl.npw + WN7_NCW; }
