@@ -10,7 +10,9 @@ echo "== pytest golden"
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "golden or block_count or batch_tiles" > gpurun_out/pytest_golden.log 2>&1; echo "pytest golden rc=$?" | tee -a gpurun_out/pytest_golden.log
 tail -25 gpurun_out/pytest_golden.log
 echo "== sweep"
-timeout 1200 python scripts/sweep.py cfg2:T=2000,WN_PROF=1 cfg2:T=2000,WN_ENGINE=5 \
+timeout 1500 python scripts/sweep.py cfg2:T=2000,WN_PROF=1 cfg2:T=2000,WN_ENGINE=5 \
+  cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=2,WN_XSTRIDE=32 cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=3,WN_XSTRIDE=32 cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=2,WN_XSTRIDE=32,WN_PROF=1 \
+  cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=64 cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=96 cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=64,WN_XC_SHIFT=2,WN_XSTRIDE=32 \
   cfg2:T=2000,WN_EX_SPREAD=0 cfg2:T=2000,WN_EX_SPREAD=3 \
   cfg2:T=2000,WN_POLL_WARPS=4 cfg2:T=2000,WN_POLL_WARPS=6 \
   cfg2:T=2000,WN_GATE_CYCLES=800 cfg2:T=2000,WN_GATE_CYCLES=1200 cfg2:T=2000,WN_GATE_CYCLES=1600 cfg2:T=2000,WN_GATE_CYCLES=2000 \

@@ -793,16 +793,66 @@ struct Engine {
 
     // One pass: two complete rows.  Lane l handles k = x_off + 4*(l + 32 j) .. +3 of both rows for every utterance,
     // the butterfly leaves value (row r, utterance b) in lane (r*BT + b) * 32/NV, and those lanes finalise.
+    // The weights of a stage do not depend on its input: the first (critical) pass of a stage keeps its first WPRE
+    // k-steps in registers, loaded BEFORE the warp waits for the input vector.
+    static constexpr int WPRE = 6;
+    __device__ __forceinline__ void preload_pass(const Wn7Pass& ps, const float* __restrict__ blob, float4 (&wa)[WPRE],
+                                                 float4 (&wb)[WPRE]) {
+        const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
+        const int nit = ps.nit;
+#pragma unroll
+        for (int u = 0; u < WPRE; ++u) {
+            if (u < nit) {
+                wa[u] = w[u * 64];
+                wb[u] = w[u * 64 + 32];
+            }
+        }
+    }
+    __device__ __forceinline__ void fma_step(const float4& wa, const float4& wb, const float* __restrict__ x, int xv,
+                                             float (&acc)[NV], float (&acc2)[NV]) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            const float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)b * xv);
+            if constexpr (BT == 1) {
+                // one utterance: two independent chains per row keep the FMA pipe busy
+                acc[0] = fmaf(wa.x, x4.x, acc[0]);
+                acc2[0] = fmaf(wa.y, x4.y, acc2[0]);
+                acc[0] = fmaf(wa.z, x4.z, acc[0]);
+                acc2[0] = fmaf(wa.w, x4.w, acc2[0]);
+                acc[1] = fmaf(wb.x, x4.x, acc[1]);
+                acc2[1] = fmaf(wb.y, x4.y, acc2[1]);
+                acc[1] = fmaf(wb.z, x4.z, acc[1]);
+                acc2[1] = fmaf(wb.w, x4.w, acc2[1]);
+            } else {
+                acc[b] = fmaf(wa.x, x4.x, acc[b]);
+                acc[b] = fmaf(wa.y, x4.y, acc[b]);
+                acc[b] = fmaf(wa.z, x4.z, acc[b]);
+                acc[b] = fmaf(wa.w, x4.w, acc[b]);
+                acc[BT + b] = fmaf(wb.x, x4.x, acc[BT + b]);
+                acc[BT + b] = fmaf(wb.y, x4.y, acc[BT + b]);
+                acc[BT + b] = fmaf(wb.z, x4.z, acc[BT + b]);
+                acc[BT + b] = fmaf(wb.w, x4.w, acc[BT + b]);
+            }
+        }
+    }
+    template <bool PRE>
     __device__ __forceinline__ void run_pass(const Wn7Pass& ps, const float* __restrict__ blob, const float* __restrict__ xb,
-                                             int s, int t, uint32_t tag) {
+                                             int s, int t, uint32_t tag, const float4 (&pwa)[WPRE], const float4 (&pwb)[WPRE]) {
         const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
         const float* __restrict__ x = xb + ps.x_off + 4 * lane;
         const int xv = pl.xin_vals;
-        float acc[NV];
+        float acc[NV], acc2[NV];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+        for (int v = 0; v < NV; ++v) { acc[v] = 0.f; acc2[v] = 0.f; }
         const int nit = ps.nit;
-        for (int j0 = 0; j0 < nit; j0 += 4) {
+        int j0 = 0;
+        if constexpr (PRE) {
+#pragma unroll
+            for (int u = 0; u < WPRE; ++u)
+                if (u < nit) fma_step(pwa[u], pwb[u], x + u * 128, xv, acc, acc2);
+            j0 = WPRE;
+        }
+        for (; j0 < nit; j0 += 4) {
             float4 wa[4], wb[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -812,22 +862,12 @@ struct Engine {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j0 + u < nit) {
-#pragma unroll
-                    for (int b = 0; b < BT; ++b) {
-                        const float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)b * xv + (j0 + u) * 128);
-                        acc[b] = fmaf(wa[u].x, x4.x, acc[b]);
-                        acc[b] = fmaf(wa[u].y, x4.y, acc[b]);
-                        acc[b] = fmaf(wa[u].z, x4.z, acc[b]);
-                        acc[b] = fmaf(wa[u].w, x4.w, acc[b]);
-                        acc[BT + b] = fmaf(wb[u].x, x4.x, acc[BT + b]);
-                        acc[BT + b] = fmaf(wb[u].y, x4.y, acc[BT + b]);
-                        acc[BT + b] = fmaf(wb[u].z, x4.z, acc[BT + b]);
-                        acc[BT + b] = fmaf(wb[u].w, x4.w, acc[BT + b]);
-                    }
-                }
-            }
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < nit) fma_step(wa[u], wb[u], x + (j0 + u) * 128, xv, acc, acc2);
+        }
+        if constexpr (BT == 1) {
+            acc[0] += acc2[0];
+            acc[1] += acc2[1];
         }
         reduce32<NV>(acc, lane);
         constexpr int LPV = 32 / NV;                      // lanes per value
@@ -912,11 +952,13 @@ struct Engine {
                 if (s <= L) blob = acquire_blob(t, s);
                 if (s == 0) wait_bar(bar_pre, (uint32_t)t & 1u, 0x02000000u);          // pre-sums of this step are built
                 if (s == 1) wait_bar(bar_x0, (uint32_t)t & 1u, 0x02000001u);           // x_0 at the owned rows is in place
+                const int begin = pl.pass_begin[kind][cw], cnt = pl.pass_count[kind][cw], crit = pl.pass_crit[kind][cw];
+                float4 pwa[WPRE], pwb[WPRE];
+                if (cnt > 0 && !dead) preload_pass(passes[begin], blob, pwa, pwb);
                 WN7_TICK(0);
                 if (!wait_bar(&bar_in[par], (n >> 1) & 1u, 0x08000000u | (uint32_t)s)) break;
                 WN7_TICK(1);
                 const float* xb = xin + (size_t)par * xin_floats;
-                const int begin = pl.pass_begin[kind][cw], cnt = pl.pass_count[kind][cw], crit = pl.pass_crit[kind][cw];
                 bool had_skip = false;
                 for (int i = 0; i < cnt; ++i) {
                     const Wn7Pass& ps = passes[begin + i];
@@ -925,7 +967,8 @@ struct Engine {
                         wait_count(s_skipcnt, (t * (L - 1) + (L - 1)) * nskip, 0x02000002u);
                         if (dead) break;
                     }
-                    run_pass(ps, blob, xb, s, t, n + 1u);
+                    if (i == 0) run_pass<true>(ps, blob, xb, s, t, n + 1u, pwa, pwb);
+                    else run_pass<false>(ps, blob, xb, s, t, n + 1u, pwa, pwb);
                     if (ps.job == WN7_J_S) had_skip = true;
                     if (i + 1 == crit) WN7_TICK(2);
                 }

@@ -172,7 +172,9 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
     pl.ex_h1 = pl.ex_sk + pl.S;
     pl.ex_h2 = pl.ex_h1 + pl.S;
     pl.ex_elems = pl.ex_h2 + pl.O;
-    pl.copy_stride_pairs = (((long long)pl.ex_elems * BT + WN_XCHUNK - 1) / WN_XCHUNK + 1) * WN_XSTRIDE + 96;
+    pl.xc_shift = env_int("WN_XC_SHIFT", 5);          // 32 pairs (256 bytes) per chunk ...
+    pl.xstride = env_int("WN_XSTRIDE", WN_XSTRIDE);   // ... 4352 bytes apart; WN_XC_SHIFT=2 WN_XSTRIDE=32 = one sector per 256-byte granule
+    pl.copy_stride_pairs = ((((long long)pl.ex_elems * BT) >> pl.xc_shift) + 2) * pl.xstride + 96;
 
     // ---- history rings: tap k (0 = oldest) is consumed (kw-1-k)*d steps later
     ringtab.assign((size_t)pl.L * std::max(pl.kw - 1, 0) * 2, 0);

@@ -81,7 +81,12 @@ struct WnPlan {
     int red1_floats;            // one of the two critical-partials buffers (alternating by stage)
     int red2_floats;            // one of the two deferred-partials buffers
     float skip_scale;           // sqrt(1/L), wavenet.py:313
+    int xc_shift, xstride;      // exchange layout: 2^xc_shift pairs per chunk, chunks xstride pairs apart
 };
+WN_HD long long wn_pair_index_(const WnPlan& pl, long long lin) {
+    return (long long)(((unsigned long long)lin >> pl.xc_shift) * (unsigned long long)pl.xstride +
+                       ((unsigned long long)lin & ((1ull << pl.xc_shift) - 1ull)));
+}
 
 // balanced split of `rows` over P blocks: block p owns [base, base+cnt)
 WN_HD void wn_part(int rows, int P, int p, int& base, int& cnt) {
@@ -96,7 +101,8 @@ WN_HD int wn_ceil_div(int a, int b) { return (a + b - 1) / b; }
 // stored in 256-byte chunks (32 pairs: what one warp polls with one load) spaced 4352 bytes apart.
 #define WN_XCHUNK 32
 #define WN_XSTRIDE 544
-WN_HD long long wn_pair_index(long long lin) { return (long long)(((unsigned long long)lin >> 5) * WN_XSTRIDE + ((unsigned long long)lin & 31ull)); }
+#define wn_pair_index(lin) wn_pair_index_(pl, (lin))
+WN_HD long long wn_pair_index_(const struct WnPlan& pl, long long lin);
 WN_HD int wn_dilation(const WnPlan& pl, int l) { return 1 << (l % pl.per_stack); }
 // exchange ids within a step (tag = t*(L+3) + id + 1)
 WN_HD int wn_eid_yx(int s) { return s; }              // (y_s, x_s), s = 0..L-1
