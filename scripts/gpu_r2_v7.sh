@@ -11,13 +11,11 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "golden or
 tail -25 gpurun_out/pytest_golden.log
 echo "== sweep"
 timeout 1500 python scripts/sweep.py cfg2:T=2000,WN_PROF=1 cfg2:T=2000,WN_ENGINE=5 \
-  cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=2,WN_XSTRIDE=32 cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=3,WN_XSTRIDE=32 cfg2:T=2000,WN_ENGINE=5,WN_XC_SHIFT=2,WN_XSTRIDE=32,WN_PROF=1 \
-  cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=64 cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=96 cfg2:T=2000,WN_ENGINE=5,WN_NUM_CTAS=64,WN_XC_SHIFT=2,WN_XSTRIDE=32 \
-  cfg2:T=2000,WN_EX_SPREAD=0 cfg2:T=2000,WN_EX_SPREAD=3 \
-  cfg2:T=2000,WN_POLL_WARPS=4 cfg2:T=2000,WN_POLL_WARPS=6 \
-  cfg2:T=2000,WN_GATE_CYCLES=800 cfg2:T=2000,WN_GATE_CYCLES=1200 cfg2:T=2000,WN_GATE_CYCLES=1600 cfg2:T=2000,WN_GATE_CYCLES=2000 \
-  cfg2:T=2000,WN_GATE_CYCLES=1200,WN_POLL_WARPS=4 cfg2:T=2000,WN_BACKOFF_NS=100 cfg2:T=2000,WN_GATE_CYCLES=1200,WN_BACKOFF_NS=100 \
-  cfg2:T=2000,B=8 cfg2:T=2000,B=4 cfg2:T=2000,B=2 cfg2:T=2000,B=8,WN_GATE_CYCLES=2000 cfg1:T=2000 cfg3:T=2000 cfg5:T=2000 > gpurun_out/sweep_r2b.log 2>&1; echo "sweep rc=$?"
+  cfg2:T=2000,WN_EX_SPREAD=0 cfg2:T=2000,WN_EX_SPREAD=3 cfg2:T=2000,WN_EX_SPREAD=2 \
+  cfg2:T=2000,WN_POLL_WARPS=8 cfg2:T=2000,WN_POLL_WARPS=8,WN_PROF=1 cfg2:T=2000,WN_POLL_WARPS=4 \
+  cfg2:T=2000,WN_GATE_CYCLES=600 cfg2:T=2000,WN_GATE_CYCLES=1000 cfg2:T=2000,WN_GATE_CYCLES=1400 \
+  cfg2:T=2000,WN_BACKOFF_NS=100 cfg2:T=2000,WN_RING_SLOTS=3 cfg2:T=2000,WN_RING_SLOTS=2 \
+  cfg2:T=2000,B=8 cfg2:T=2000,B=4 cfg2:T=2000,B=2 cfg2:T=2000,B=8,WN_POLL_WARPS=8 cfg1:T=2000 cfg3:T=2000 cfg5:T=2000 > gpurun_out/sweep_r2b.log 2>&1; echo "sweep rc=$?"
 cat gpurun_out/sweep_r2b.log
 echo "== pytest all"
 timeout ${PYTEST_TIMEOUT:-1200} python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log

@@ -45,9 +45,11 @@ def model_for(scales, cin_pad, net="ConvInUpsampleNetwork", C=80):
 def test_native_upsampler_matches_module(scales, cin_pad, net, frames):
     m = model_for(scales, cin_pad, net)
     B = 3
+    import copy
     c = torch.randn(B, 80, frames + 2 * cin_pad).cuda()
     with torch.no_grad():
-        ref = m.upsample_net(c)                                   # (B,C,T) PyTorch module with the reference's structure
+        # fp32 reference on the CPU: cuDNN would run the conv_in / smoothing convolutions in TF32 by default
+        ref = copy.deepcopy(m.upsample_net).cpu()(c.cpu()).cuda()    # (B,C,T) module with the reference's structure
     T = ref.size(-1)
     eng = m._get_engine()
     assert m._native_upsample and eng.upsampled_length(c.size(-1)) == T

@@ -80,9 +80,11 @@ static int32_t build_plan7(const wn_config& c, int batch, int num_sms, long long
     pl.xoff = align_up7(pl.G2, 4);
     // polling warps: one 16-byte load (2 pairs) per lane for the (y, x) vector of one utterance, capped
     {
-        int want = c.poll_warps > 0 ? c.poll_warps : env_int("WN_POLL_WARPS", 0);
-        if (want <= 0) want = wn7_ceil_div((pl.G2 + pl.R) / 2, 32);
-        pl.npw = std::max(2, std::min(WN7_MAX_NPW, want));
+        // poll_warps: -1 (or WN_POLL_WARPS=-1 / "self") = compute warps 0..3 poll themselves; 0 = choose
+        int want = c.poll_warps != 0 ? c.poll_warps : env_int("WN_POLL_WARPS", 0);
+        if (want == 0) want = env_int("WN_POLL_DEFAULT", -1);
+        if (want < 0) pl.npw = 0;
+        else pl.npw = std::max(2, std::min(WN7_MAX_NPW, want));
     }
     pl.nthreads = 32 * (pl.npw + WN7_NCW + 3);
 

@@ -145,7 +145,7 @@ __device__ __forceinline__ float u01(uint32_t r) {   // (0,1), then mapped like 
 }
 
 // slow path of every spin loop: has another block faulted / have we waited too long?
-__device__ __noinline__ bool check_abort_slow(volatile int* s_abort, int* err, long long timeout, uint32_t what, int p,
+__device__ __forceinline__ bool check_abort_slow(volatile int* s_abort, int* err, long long timeout, uint32_t what, int p,
                                               long long& t0) {
     if (*s_abort) return true;
     if (ld_flag(err) != 0) {
@@ -193,23 +193,53 @@ __device__ __forceinline__ void reduce32(float (&v)[NV], int lane) {
     }
 }
 
-template <int BT>
+#define WN7_NSP 4                 // compute warps that poll when there are no dedicated polling warps
+
+// SELF: no dedicated polling warps -- compute warps 0..WN7_NSP-1 poll the vector themselves (their share each), meet
+// at a named barrier and go straight into their passes; the other compute warps are released through the mbarrier.
+template <int BT, bool SELF>
 struct Engine {
     static constexpr int NV = 2 * BT;          // values of one pass: 2 rows x BT utterances, index r*BT + b
     const Wn7Plan& pl;
     const Wn7Ptrs& pp;
     unsigned char* sm;
     int tid, warp, lane, p;
-    uint64_t *bar_full, *bar_empty, *bar_cfull, *bar_cempty, *bar_in, *bar_free, *bar_pre, *bar_x0, *bar_ps, *bar_dstep;
-    volatile int* s_abort;
-    volatile int* s_skipcnt;       // skip-row passes completed (monotonic)
-    Wn7Pass* passes;
-    int* ringtab;                  // [e][3]: offset, delay, t mod delay
-    float *xin, *sb, *pre, *cond, *bias, *skipacc, *xown, *x0own, *hs, *noise, *x0w, *slots;
-    volatile float* ring;
-    float* s_in;      // [BT] scalar feedback
-    int* s_idx;       // [BT] class feedback
-    float* s_dense;   // [BT][O] dense feedback
+    // Shared-memory regions are addressed through accessors that recompute `sm + offset` from the plan (a uniform
+    // constant-bank load) instead of ~30 pointer members that would stay live in registers across the whole loop.
+    template <typename T> __device__ __forceinline__ T* at(int off) const { return reinterpret_cast<T*>(sm + off); }
+    __device__ __forceinline__ uint64_t* bar_full_() const { return at<uint64_t>(pl.sm_bar); }
+    __device__ __forceinline__ uint64_t* bar_empty_() const { return bar_full_() + pl.nres + pl.nring; }
+    __device__ __forceinline__ uint64_t* bar_cfull_() const { return bar_empty_() + (pl.nring > 0 ? pl.nring : 1); }
+    __device__ __forceinline__ uint64_t* bar_cempty_() const { return bar_cfull_() + 2; }
+    __device__ __forceinline__ uint64_t* bar_in_() const { return bar_cfull_() + 4; }
+    __device__ __forceinline__ uint64_t* bar_free_() const { return bar_cfull_() + 6; }
+    __device__ __forceinline__ uint64_t* bar_pre_() const { return bar_cfull_() + 8; }
+    __device__ __forceinline__ uint64_t* bar_x0_() const { return bar_cfull_() + 9; }
+    __device__ __forceinline__ uint64_t* bar_ps_() const { return bar_cfull_() + 10; }
+    __device__ __forceinline__ uint64_t* bar_dstep_() const { return bar_cfull_() + 11; }
+    __device__ __forceinline__ volatile int* s_abort_() const { return at<volatile int>(pl.sm_misc); }
+    __device__ __forceinline__ volatile int* s_skipcnt_() const { return at<volatile int>(pl.sm_misc) + 1; }   // skip-row passes_() completed
+    __device__ __forceinline__ Wn7Pass* passes_() const { return at<Wn7Pass>(pl.sm_pass); }
+    __device__ __forceinline__ int* ringtab_() const { return at<int>(pl.sm_ringtab); }       // [e][3]: offset, delay, t mod delay
+    __device__ __forceinline__ float* xin_() const { return at<float>(pl.sm_xin); }
+    __device__ __forceinline__ float* sb_() const { return at<float>(pl.sm_sb); }
+    __device__ __forceinline__ float* pre_() const { return at<float>(pl.sm_pre); }
+    __device__ __forceinline__ float* cond_() const { return at<float>(pl.sm_cond); }
+    __device__ __forceinline__ float* bias_() const { return at<float>(pl.sm_bias); }
+    __device__ __forceinline__ float* skipacc_() const { return at<float>(pl.sm_skipacc); }
+    __device__ __forceinline__ float* xown_() const { return at<float>(pl.sm_xown); }
+    __device__ __forceinline__ float* x0own_() const { return at<float>(pl.sm_xown) + pl.mx * BT; }
+    __device__ __forceinline__ float* hs_() const { return at<float>(pl.sm_hs); }
+    __device__ __forceinline__ float* noise_() const { return at<float>(pl.sm_noise); }
+    __device__ __forceinline__ float* x0w_() const { return at<float>(pl.sm_x0w); }
+    __device__ __forceinline__ float* slots_() const { return at<float>(pl.sm_slots); }
+    __device__ __forceinline__ volatile float* ring_() const {
+        return pl.ring_in_smem ? at<volatile float>(pl.sm_ring)
+                               : (volatile float*)(pp.ring_g + (size_t)p * pl.ring_pos_total * 4 * pl.qA * BT);
+    }
+    __device__ __forceinline__ float* s_in_() const { return at<float>(pl.sm_in); }                  // [BT] scalar feedback
+    __device__ __forceinline__ int* s_idx_() const { return at<int>(pl.sm_in) + BT; }                // [BT] class feedback
+    __device__ __forceinline__ float* s_dense_() const { return at<float>(pl.sm_in) + 2 * BT; }      // [BT][O] dense feedback
     bool dead;
     // rows this block owns
     int y0, ny, x0r, nx, s0, ns, a0, na, b0, nb;
@@ -219,40 +249,6 @@ struct Engine {
         warp = tid >> 5;
         lane = tid & 31;
         p = blockIdx.x;
-        const int nslots = pl.nres + pl.nring;
-        bar_full = reinterpret_cast<uint64_t*>(sm + pl.sm_bar);
-        bar_empty = bar_full + nslots;
-        bar_cfull = bar_empty + (pl.nring > 0 ? pl.nring : 1);
-        bar_cempty = bar_cfull + 2;
-        bar_in = bar_cempty + 2;
-        bar_free = bar_in + 2;
-        bar_pre = bar_free + 2;
-        bar_x0 = bar_pre + 1;
-        bar_ps = bar_x0 + 1;
-        bar_dstep = bar_ps + 1;
-        s_abort = reinterpret_cast<volatile int*>(sm + pl.sm_misc);
-        s_skipcnt = s_abort + 1;
-        passes = reinterpret_cast<Wn7Pass*>(sm + pl.sm_pass);
-        ringtab = reinterpret_cast<int*>(sm + pl.sm_ringtab);
-        xin = reinterpret_cast<float*>(sm + pl.sm_xin);
-        sb = reinterpret_cast<float*>(sm + pl.sm_sb);
-        pre = reinterpret_cast<float*>(sm + pl.sm_pre);
-        cond = reinterpret_cast<float*>(sm + pl.sm_cond);
-        bias = reinterpret_cast<float*>(sm + pl.sm_bias);
-        skipacc = reinterpret_cast<float*>(sm + pl.sm_skipacc);
-        xown = reinterpret_cast<float*>(sm + pl.sm_xown);
-        x0own = xown + pl.mx * BT;
-        hs = reinterpret_cast<float*>(sm + pl.sm_hs);
-        noise = reinterpret_cast<float*>(sm + pl.sm_noise);
-        s_in = reinterpret_cast<float*>(sm + pl.sm_in);
-        s_idx = reinterpret_cast<int*>(s_in + BT);
-        s_dense = reinterpret_cast<float*>(s_idx + BT);
-        x0w = reinterpret_cast<float*>(sm + pl.sm_x0w);
-        slots = reinterpret_cast<float*>(sm + pl.sm_slots);
-        if (pl.ring_in_smem)
-            ring = reinterpret_cast<volatile float*>(sm + pl.sm_ring);
-        else
-            ring = pp.ring_g + (size_t)p * pl.ring_pos_total * 2 * pl.my * BT;
         dead = false;
         wn7_part(pl.G2, pl.P, p, y0, ny);
         wn7_part(pl.R, pl.P, p, x0r, nx);
@@ -263,7 +259,7 @@ struct Engine {
 
     // ---- watchdog: a stuck wait sets the device fault word and makes every block unwind
     __device__ __forceinline__ bool check_abort(uint32_t what, long long& t0) {
-        return check_abort_slow(s_abort, pp.err, pp.timeout_cycles, what, p, t0);
+        return check_abort_slow(s_abort_(), pp.err, pp.timeout_cycles, what, p, t0);
     }
     // Waits are WARP-COLLECTIVE (all 32 lanes call them together) and return a warp-uniform verdict, so that a
     // watchdog abort never leaves some lanes of a warp behind in a later shuffle or vote.  `relaxed` waits
@@ -316,11 +312,27 @@ struct Engine {
     // barrier over the polling warps with a watchdog (a plain bar.sync would hang if one of them aborted)
     uint32_t ps_par = 0;
     __device__ __forceinline__ void poller_sync() {
-        __syncwarp();
-        if (!dead && lane == 0) mbar_arrive(bar_ps);          // one arrival per polling warp
-        wait_bar(bar_ps, ps_par, 0x00200000u);
-        ps_par ^= 1u;
+        if constexpr (SELF) {
+            // named barrier over the polling compute warps that also OR-reduces the abort flag: every thread always
+            // reaches it (all spin loops have a watchdog), so an abort cannot leave a warp behind
+            uint32_t r;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.u32 p, %1, 0;\n\t"
+                "bar.red.or.pred q, 1, %2, p;\n\t"
+                "selp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(r)
+                : "r"((uint32_t)dead), "n"(32 * WN7_NSP)
+                : "memory");
+            dead = r != 0;
+        } else {
+            __syncwarp();
+            if (!dead && lane == 0) mbar_arrive(bar_ps_());          // one arrival per polling warp
+            wait_bar(bar_ps_(), ps_par, 0x00200000u);
+            ps_par ^= 1u;
+        }
     }
+    __device__ __forceinline__ int n_poll_warps() const { return SELF ? WN7_NSP : pl.npw; }
     // `slot` = pair offset of the stage slot, `i` = linear pair index inside it
     __device__ __forceinline__ void publish(long long slot, long long i, float v, uint32_t tag) {
         st_pair(pp.xbuf + slot + wn7_phys(pl, i), v, tag);
@@ -334,8 +346,8 @@ struct Engine {
         const float* base = pp.wpack + (size_t)p * pl.cta_w_floats;
         for (int i = 0; i < pl.nres; ++i) {
             const uint32_t bytes = (uint32_t)wn7_blob_floats(pl, i) * 4u;
-            mbar_expect_tx(&bar_full[i], bytes);
-            bulk_g2s(slots + (size_t)i * pl.slot_floats, base + wn7_blob_off(pl, i), bytes, &bar_full[i]);
+            mbar_expect_tx(&bar_full_()[i], bytes);
+            bulk_g2s(slots_() + (size_t)i * pl.slot_floats, base + wn7_blob_off(pl, i), bytes, &bar_full_()[i]);
         }
         const int nstream = pl.nblobs - pl.nres;
         if (nstream <= 0) return;
@@ -344,29 +356,30 @@ struct Engine {
         uint32_t s = 0, u = 0;
         for (uint32_t js = 0; js < total; ++js) {
             if (u > 0) {
-                if (!wait_bar_lane<true>(&bar_empty[s], (u - 1) & 1u, 0x40000000u | s)) return;
+                if (!wait_bar_lane<true>(&bar_empty_()[s], (u - 1) & 1u, 0x40000000u | s)) return;
             }
             const uint32_t bytes = (uint32_t)wn7_blob_floats(pl, i) * 4u;
-            uint64_t* fb = &bar_full[pl.nres + s];
+            uint64_t* fb = &bar_full_()[pl.nres + s];
             mbar_expect_tx(fb, bytes);
-            bulk_g2s(slots + (size_t)(pl.nres + s) * pl.slot_floats, base + wn7_blob_off(pl, i), bytes, fb);
+            bulk_g2s(slots_() + (size_t)(pl.nres + s) * pl.slot_floats, base + wn7_blob_off(pl, i), bytes, fb);
             if (++i == pl.nblobs) i = pl.nres;
             if (++s == (uint32_t)pl.nring) { s = 0; ++u; }
         }
     }
 
     // ======================================================================================
-    // conditioning warp: cond[t&1][l][row][b] = Wc_l[the block's gate rows] . c_t  (modules.py:141-145), one step
+    // conditioning warp: cond_()[t&1][l][row][b] = Wc_l[the block's gate rows] . c_t  (modules.py:141-145), one step
     // ahead; the weights come straight from L2 (they are read once per step)
     // ======================================================================================
     __device__ void cond_loop() {
         const int C = pl.C, L = pl.L, T = pp.T, B = pp.B, RA4 = 4 * pl.qA;
-        constexpr int M = ilog2c(NV);
+        constexpr int NVC = 4 * BT;                 // one row QUAD x BT utterances (the passes use row pairs)
+        constexpr int M = ilog2c(NVC);
         const float* cw = pp.cwpack + (size_t)p * pl.cta_cw_floats;
         for (int t = 0; t < T; ++t) {
             const int par = t & 1, u = t >> 1;
             if (u > 0) {
-                if (!wait_bar<true>(&bar_cempty[par], (u - 1) & 1u, 0x20000000u)) return;
+                if (!wait_bar<true>(&bar_cempty_()[par], (u - 1) & 1u, 0x20000000u)) return;
             }
             float ct[BT][WN7_MAX_CI];
 #pragma unroll
@@ -376,12 +389,12 @@ struct Engine {
                     const int ch = lane + 32 * i;
                     ct[b][i] = (b < B && ch < C) ? __ldg(pp.c + ((size_t)b * T + t) * C + ch) : 0.f;
                 }
-            float* dst = cond + (size_t)par * L * RA4 * BT;
+            float* dst = cond_() + (size_t)par * L * RA4 * BT;
             for (int l = 0; l < L; ++l) {
                 for (int q = 0; q < pl.qA; ++q) {
-                    float acc[NV];
+                    float acc[NVC];
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+                    for (int v = 0; v < NVC; ++v) acc[v] = 0.f;
                     const float* wq = cw + ((size_t)(l * pl.qA + q) * C) * 4;
 #pragma unroll
                     for (int i = 0; i < WN7_MAX_CI; ++i) {
@@ -399,14 +412,14 @@ struct Engine {
                     }
                     // full-warp butterfly (32 lanes): one more level than reduce16
                     {
-                        int n = NV;
+                        int n = NVC;
 #pragma unroll
                         for (int off = 16; off >= 1; off >>= 1) {
                             if (n > 1) {
                                 n >>= 1;
                                 const bool hi = (lane & off) != 0;
 #pragma unroll
-                                for (int i = 0; i < NV / 2; ++i) {
+                                for (int i = 0; i < NVC / 2; ++i) {
                                     if (i < n) {
                                         const float send = hi ? acc[i] : acc[i + n];
                                         const float keep = hi ? acc[i + n] : acc[i];
@@ -425,7 +438,7 @@ struct Engine {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_cfull[par]);
+            if (lane == 0) mbar_arrive(&bar_cfull_()[par]);
         }
     }
 
@@ -443,9 +456,9 @@ struct Engine {
             }
         }
     }
-    // noise for step t of utterance b into noise[b][*]; layout [u1(0..K-1) | u2 or z] or [e(0..O-1)]
+    // noise_() for step t of utterance b into noise_()[b][*]; layout [u1(0..K-1) | u2 or z] or [e(0..O-1)]
     __device__ void fetch_noise(int t, int b) {
-        float* nz = noise + (size_t)b * (pl.O + 2);
+        float* nz = noise_() + (size_t)b * (pl.O + 2);
         const int B = pp.Btot, K = pl.Kmix, O = pl.O;
         const uint32_t ub = (uint32_t)(pp.b0 + b);
         const bool replay = pp.noise_kind == 0;
@@ -490,39 +503,39 @@ struct Engine {
             nz[K] = v;
         }
     }
-    // draw sample of utterance b from hs[:, b]; sets the feedback for step t+1 and writes outputs
+    // draw sample of utterance b from hs_()[:, b]; sets the feedback for step t+1 and writes outputs
     __device__ void sample_utt(int t, int b) {
         const int O = pl.O, K = pl.Kmix, T = pp.T;
-        const float* nz = noise + (size_t)b * (pl.O + 2);
+        const float* nz = noise_() + (size_t)b * (pl.O + 2);
         const bool writer = (p == 0);
         if (pl.head_kind == 2) {
             const bool softmax = (pp.flags & WN7_FLAG_SOFTMAX) != 0, quant = (pp.flags & WN7_FLAG_QUANTIZE) != 0;
             // F.softmax (wavenet.py:332): exp(h - max) / sum
             if (softmax) {
                 float m = -INFINITY;
-                for (int i = lane; i < O; i += 32) m = fmaxf(m, hs[i * BT + b]);
+                for (int i = lane; i < O; i += 32) m = fmaxf(m, hs_()[i * BT + b]);
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
                 float s = 0.f;
                 for (int i = lane; i < O; i += 32) {
-                    const float e = expf(hs[i * BT + b] - m);
-                    hs[i * BT + b] = e;
+                    const float e = expf(hs_()[i * BT + b] - m);
+                    hs_()[i * BT + b] = e;
                     s += e;
                 }
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                for (int i = lane; i < O; i += 32) hs[i * BT + b] = hs[i * BT + b] / s;
+                for (int i = lane; i < O; i += 32) hs_()[i * BT + b] = hs_()[i * BT + b] / s;
             }
             if (quant) {
                 // OneHotCategorical(p).sample() (wavenet.py:334-335): renormalise, argmax(p / Exp(1))
                 float sp = 0.f;
-                for (int i = lane; i < O; i += 32) sp += hs[i * BT + b];
+                for (int i = lane; i < O; i += 32) sp += hs_()[i * BT + b];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, off);
                 float best = -INFINITY;
                 int bi = 0x7fffffff;
                 for (int i = lane; i < O; i += 32) {
-                    const float r = (hs[i * BT + b] / sp) / nz[i];
+                    const float r = (hs_()[i * BT + b] / sp) / nz[i];
                     if (r > best) {
                         best = r;
                         bi = i;
@@ -532,24 +545,24 @@ struct Engine {
                 if (bi >= O) bi = 0;
                 if (lane == 0) {
                     if (writer && b < pp.B) pp.out_index[(size_t)b * T + t] = bi;
-                    s_idx[b] = (t + 1 < pp.T_test && b < pp.B) ? (pp.test_index ? pp.test_index[(size_t)b * pp.T_test + t + 1] : -1)
+                    s_idx_()[b] = (t + 1 < pp.T_test && b < pp.B) ? (pp.test_index ? pp.test_index[(size_t)b * pp.T_test + t + 1] : -1)
                                                                : bi;
                 }
             } else {
                 for (int i = lane; i < O; i += 32) {
-                    const float v = hs[i * BT + b];
+                    const float v = hs_()[i * BT + b];
                     if (writer && b < pp.B) pp.out_dense[((size_t)b * O + i) * T + t] = v;
-                    s_dense[b * O + i] = v;
+                    s_dense_()[b * O + i] = v;
                 }
                 if (lane == 0)
-                    s_idx[b] = (t + 1 < pp.T_test && b < pp.B && pp.test_index)
+                    s_idx_()[b] = (t + 1 < pp.T_test && b < pp.B && pp.test_index)
                                    ? pp.test_index[(size_t)b * pp.T_test + t + 1] : -1;
             }
             // teacher forcing with dense rows overrides the feedback
             if (t + 1 < pp.T_test && pp.test_dense != nullptr && b < pp.B) {
                 for (int i = lane; i < O; i += 32)
-                    s_dense[b * O + i] = pp.test_dense[((size_t)b * pp.T_test + t + 1) * O + i];
-                if (lane == 0) s_idx[b] = -1;
+                    s_dense_()[b * O + i] = pp.test_dense[((size_t)b * pp.T_test + t + 1) * O + i];
+                if (lane == 0) s_idx_()[b] = -1;
             }
             return;
         }
@@ -561,7 +574,7 @@ struct Engine {
             float best = -INFINITY;
             int bi = 0x7fffffff;
             for (int i = lane; i < K; i += 32) {
-                const float g = hs[i * BT + b] - logf(-logf(nz[i]));
+                const float g = hs_()[i * BT + b] - logf(-logf(nz[i]));
                 if (g > best) {
                     best = g;
                     bi = i;
@@ -569,14 +582,14 @@ struct Engine {
             }
             warp_argmax(best, bi);
             if (bi >= K) bi = 0;
-            mean = hs[(K + bi) * BT + b];        // mixture.py:143-146 one-hot select
-            ls = hs[(2 * K + bi) * BT + b];
+            mean = hs_()[(K + bi) * BT + b];        // mixture.py:143-146 one-hot select
+            ls = hs_()[(2 * K + bi) * BT + b];
         } else if (O == 2) {
-            mean = hs[0 * BT + b];               // mixture.py:258-259
-            ls = hs[1 * BT + b];
+            mean = hs_()[0 * BT + b];               // mixture.py:258-259
+            ls = hs_()[1 * BT + b];
         } else {
-            mean = hs[1 * BT + b];               // mixture.py:260-261 (C == 3)
-            ls = hs[2 * BT + b];
+            mean = hs_()[1 * BT + b];               // mixture.py:260-261 (C == 3)
+            ls = hs_()[2 * BT + b];
         }
         float xv;
         if (pl.head_kind == 0) {
@@ -590,14 +603,14 @@ struct Engine {
         xv = fminf(fmaxf(xv, -1.0f), 1.0f);      // mixture.py:154 / :269
         if (lane == 0) {
             if (writer && b < pp.B) pp.out_scalar[(size_t)b * T + t] = xv;
-            s_in[b] = (t + 1 < pp.T_test && b < pp.B) ? pp.test_scalar[(size_t)b * pp.T_test + t + 1] : xv;
+            s_in_()[b] = (t + 1 < pp.T_test && b < pp.B) ? pp.test_scalar[(size_t)b * pp.T_test + t + 1] : xv;
         }
     }
 
     // ======================================================================================
     // pollers
     // ======================================================================================
-    // copy pairs [p0, p0+npairs) of exchange slot `src` into xin (utterance-major) once every tag equals `tag`;
+    // copy pairs [p0, p0+npairs) of exchange slot `src` into xin_() (utterance-major) once every tag equals `tag`;
     // lane pl_ of NPL takes 16-byte loads j = pl_, pl_+NPL, ... (4 of them in flight per retry round)
     __device__ void poll_pairs(const uint2* __restrict__ src, int p0, int npairs, uint32_t tag, float* __restrict__ xb, int pl_,
                                int NPL) {
@@ -645,7 +658,7 @@ struct Engine {
         dead = __any_sync(0xffffffffu, dead);
     }
     // x_0 = first 1x1 conv of the fed-back sample (wavenet.py:308): all R entries -> xb[b][xoff + k], and the rows the
-    // block owns -> x0own
+    // block owns -> x0own_()
     __device__ void write_x0(float* __restrict__ xb, int pl_, int NPL, bool own_too) {
         const int R = pl.R, O = pl.O, xv = pl.xin_vals;
         const int n = R * BT, nown = pl.mx * BT;
@@ -656,25 +669,25 @@ struct Engine {
             float v = 0.f;
             if (g >= 0) {
                 if (pl.input_kind == 0) {
-                    v = fmaf(x0w[g], s_in[b], x0w[R + g]);
+                    v = fmaf(x0w_()[g], s_in_()[b], x0w_()[R + g]);
                 } else {
-                    const int idx = min(s_idx[b], O - 1);          // class ids are range-checked on the host where it can
+                    const int idx = min(s_idx_()[b], O - 1);          // class ids are range-checked on the host where it can
                     if (idx >= 0) {
-                        v = __ldg(pp.first_w + (size_t)idx * R + g) + x0w[R + g];   // one-hot input: a column gather
+                        v = __ldg(pp.first_w + (size_t)idx * R + g) + x0w_()[R + g];   // one-hot input: a column gather
                     } else {
                         float a = 0.f;
-                        for (int o = 0; o < O; ++o) a = fmaf(__ldg(pp.first_w + (size_t)o * R + g), s_dense[b * O + o], a);
-                        v = a + x0w[R + g];
+                        for (int o = 0; o < O; ++o) a = fmaf(__ldg(pp.first_w + (size_t)o * R + g), s_dense_()[b * O + o], a);
+                        v = a + x0w_()[R + g];
                     }
                 }
             }
-            if (own) x0own[k * BT + b] = v;
+            if (own) x0own_()[k * BT + b] = v;
             else xb[b * xv + pl.xoff + k] = v;
         }
     }
-    // all head outputs of step t -> hs, then the sampler (sets the feedback of step t+1)
+    // all head outputs of step t -> hs_(), then the sampler (sets the feedback of step t+1)
     __device__ void read_head_and_sample(int t, int pl_, int NPL) {
-        const int npairs = pl.O * BT;                      // pair index o*BT + b == hs index
+        const int npairs = pl.O * BT;                      // pair index o*BT + b == hs_() index
         const uint32_t tag = (uint32_t)t * (uint32_t)pl.NS + (uint32_t)(pl.L + 2) + 1u;
         const uint2* src = pp.xbuf + wn7_ex_off(pl, pl.L + 2);
         const int nld = (npairs + 1) >> 1;
@@ -693,8 +706,8 @@ struct Engine {
                 }
             }
             if (dead) break;
-            hs[2 * j] = __uint_as_float(q.x);
-            if (two) hs[2 * j + 1] = __uint_as_float(q.z);
+            hs_()[2 * j] = __uint_as_float(q.x);
+            if (two) hs_()[2 * j + 1] = __uint_as_float(q.z);
         }
         dead = __any_sync(0xffffffffu, dead);
         poller_sync();
@@ -703,23 +716,49 @@ struct Engine {
             const int O = pl.O, T = pp.T;
             for (int i = pl_; i < O * BT; i += NPL) {
                 const int o = i / BT, b = i % BT;
-                if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
+                if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs_()[i];
             }
-            if (pl.head_kind == 2) {                         // the softmax sampler overwrites hs in place
+            if (pl.head_kind == 2) {                         // the softmax sampler overwrites hs_() in place
                 poller_sync();
                 if (dead) return;
             }
         }
-        for (int b = warp; b < BT; b += pl.npw) {
+        for (int b = warp; b < BT; b += n_poll_warps()) {      // polling warps are warps 0..n-1 in both modes
             sample_utt(t, b);
             if (t + 1 < pp.T) fetch_noise(t + 1, b);
         }
         poller_sync();
     }
 
+    // poller duties of stage s of step t (global stage n), in two phases: the rare heavy work first (sampler of the
+    // previous step, x_0), then only the coherent loads -- so that a compute warp that polls can hold its preloaded
+    // weights in registers across the second phase
+    __device__ __forceinline__ void poll_stage_head(int t, int s, float* __restrict__ xb, int pl_, int NPL) {
+        if (s == 0) {
+            if (t > 0) read_head_and_sample(t - 1, pl_, NPL);
+            if (dead) return;
+            write_x0(xb, pl_, NPL, true);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_x0_());     // x_0 at the rows this block owns is in place (read in stage 1)
+        } else if (s == 1) {
+            write_x0(xb, pl_, NPL, false);              // x_0 is evaluated locally
+        }
+    }
+    __device__ __forceinline__ void poll_stage_loads(int s, uint32_t n, float* __restrict__ xb, int pl_, int NPL) {
+        if (s == 0) return;
+        const uint2* src = pp.xbuf + wn7_ex_off(pl, s - 1);
+        if (s <= pl.L) {
+            poll_pairs(src, 0, pl.G2 * BT, n, xb, pl_, NPL);
+            if (dead || s == 1) return;
+            poll_pairs(src, pl.xoff * BT, pl.R * BT, n, xb, pl_, NPL);
+        } else {
+            poll_pairs(src, 0, pl.S * BT, n, xb, pl_, NPL);
+        }
+    }
+
     __device__ void poll_loop() {
         const int NPL = 32 * pl.npw;
-        const int pl_ = warp * 32 + lane, NS = pl.NS, L = pl.L, T = pp.T;
+        const int pl_ = warp * 32 + lane, NS = pl.NS, T = pp.T;
         const int xin_floats = pl.xin_vals * BT;
         uint32_t n = 0;
         long long t_prev = clock64();
@@ -727,32 +766,17 @@ struct Engine {
             for (int s = 0; s < NS; ++s, ++n) {
                 const int par = n & 1;
                 if (n >= 2) {
-                    if (!wait_bar(&bar_free[par], ((n >> 1) - 1) & 1u, 0x10000000u | (uint32_t)s)) break;
+                    if (!wait_bar(&bar_free_()[par], ((n >> 1) - 1) & 1u, 0x10000000u | (uint32_t)s)) break;
                 }
-                float* xb = xin + (size_t)par * xin_floats;
+                float* xb = xin_() + (size_t)par * xin_floats;
                 // gate: the next vector cannot be complete earlier than the local chain + one L2 hop after this one, and
                 // polling earlier only loads the L2 slices the publishers are writing to
                 if (pl.gate_cycles > 0) { while (clock64() - t_prev < pl.gate_cycles) {} }
-                if (s == 0) {
-                    if (t > 0) read_head_and_sample(t - 1, pl_, NPL);
-                    if (dead) break;
-                    write_x0(xb, pl_, NPL, true);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_x0);     // x_0 at the rows this block owns is in place (read in stage 1)
-                } else {
-                    const uint2* src = pp.xbuf + wn7_ex_off(pl, s - 1);
-                    if (s <= L) {
-                        poll_pairs(src, 0, pl.G2 * BT, n, xb, pl_, NPL);
-                        if (dead) break;
-                        if (s == 1) write_x0(xb, pl_, NPL, false);                    // x_0 is evaluated locally
-                        else poll_pairs(src, pl.xoff * BT, pl.R * BT, n, xb, pl_, NPL);
-                    } else {
-                        poll_pairs(src, 0, pl.S * BT, n, xb, pl_, NPL);
-                    }
-                    if (dead) break;
-                }
+                poll_stage_head(t, s, xb, pl_, NPL);
+                if (!dead) poll_stage_loads(s, n, xb, pl_, NPL);
+                if (dead) break;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_in[par]);     // one arrival per polling warp
+                if (lane == 0) mbar_arrive(&bar_in_()[par]);     // one arrival per polling warp
                 t_prev = clock64();
             }
         }
@@ -766,17 +790,17 @@ struct Engine {
     uint32_t rs_par = 0;
     __device__ __forceinline__ const float* acquire_blob(int t, int i) {
         if (i < pl.nres) {
-            if (t == 0) wait_bar(&bar_full[i], 0, 0x80000000u | (uint32_t)i);
-            return slots + (size_t)i * pl.slot_floats;
+            if (t == 0) wait_bar(&bar_full_()[i], 0, 0x80000000u | (uint32_t)i);
+            return slots_() + (size_t)i * pl.slot_floats;
         }
         const int slot = pl.nres + rs_slot;
-        wait_bar(&bar_full[slot], rs_par, 0x80000000u | (uint32_t)i);
-        return slots + (size_t)slot * pl.slot_floats;
+        wait_bar(&bar_full_()[slot], rs_par, 0x80000000u | (uint32_t)i);
+        return slots_() + (size_t)slot * pl.slot_floats;
     }
     __device__ __forceinline__ void release_blob(int i) {
         if (i >= pl.nres) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[rs_slot]);
+            if (lane == 0) mbar_arrive(&bar_empty_()[rs_slot]);
             if (++rs_slot == pl.nring) {
                 rs_slot = 0;
                 rs_par ^= 1u;
@@ -793,21 +817,6 @@ struct Engine {
 
     // One pass: two complete rows.  Lane l handles k = x_off + 4*(l + 32 j) .. +3 of both rows for every utterance,
     // the butterfly leaves value (row r, utterance b) in lane (r*BT + b) * 32/NV, and those lanes finalise.
-    // The weights of a stage do not depend on its input: the first (critical) pass of a stage keeps its first WPRE
-    // k-steps in registers, loaded BEFORE the warp waits for the input vector.
-    static constexpr int WPRE = 6;
-    __device__ __forceinline__ void preload_pass(const Wn7Pass& ps, const float* __restrict__ blob, float4 (&wa)[WPRE],
-                                                 float4 (&wb)[WPRE]) {
-        const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
-        const int nit = ps.nit;
-#pragma unroll
-        for (int u = 0; u < WPRE; ++u) {
-            if (u < nit) {
-                wa[u] = w[u * 64];
-                wb[u] = w[u * 64 + 32];
-            }
-        }
-    }
     __device__ __forceinline__ void fma_step(const float4& wa, const float4& wb, const float* __restrict__ x, int xv,
                                              float (&acc)[NV], float (&acc2)[NV]) {
 #pragma unroll
@@ -835,23 +844,20 @@ struct Engine {
             }
         }
     }
-    template <bool PRE>
     __device__ __forceinline__ void run_pass(const Wn7Pass& ps, const float* __restrict__ blob, const float* __restrict__ xb,
-                                             int s, int t, uint32_t tag, const float4 (&pwa)[WPRE], const float4 (&pwb)[WPRE]) {
-        const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
-        const float* __restrict__ x = xb + ps.x_off + 4 * lane;
-        const int xv = pl.xin_vals;
+                                             int s, uint32_t tag) {
         float acc[NV], acc2[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { acc[v] = 0.f; acc2[v] = 0.f; }
+        run_pass_tail(ps, blob, xb, s, tag, 0, acc, acc2);
+    }
+    // k-steps [j0, nit) with the weights read from shared memory, then the butterfly and the finalisation
+    __device__ __forceinline__ void run_pass_tail(const Wn7Pass& ps, const float* __restrict__ blob, const float* __restrict__ xb,
+                                                  int s, uint32_t tag, int j0, float (&acc)[NV], float (&acc2)[NV]) {
+        const float4* __restrict__ w = reinterpret_cast<const float4*>(blob + ps.w_off) + lane;
+        const float* __restrict__ x = xb + ps.x_off + 4 * lane;
+        const int xv = pl.xin_vals;
         const int nit = ps.nit;
-        int j0 = 0;
-        if constexpr (PRE) {
-#pragma unroll
-            for (int u = 0; u < WPRE; ++u)
-                if (u < nit) fma_step(pwa[u], pwb[u], x + u * 128, xv, acc, acc2);
-            j0 = WPRE;
-        }
         for (; j0 < nit; j0 += 4) {
             float4 wa[4], wb[4];
 #pragma unroll
@@ -883,53 +889,52 @@ struct Engine {
             case WN7_J_A0:
             case WN7_J_A: {
                 if (r != 0 || idx >= ny) break;
-                const float a = mine + pre[((size_t)s * RA4 + 2 * idx) * BT + b];
-                const float g = other + pre[((size_t)s * RA4 + 2 * idx + 1) * BT + b];
+                const float a = mine + pre_()[((size_t)s * RA4 + 2 * idx) * BT + b];
+                const float g = other + pre_()[((size_t)s * RA4 + 2 * idx + 1) * BT + b];
                 publish(ex, (long long)(y0 + idx) * BT + b, gate(a, g), tag);
             } break;
             case WN7_J_B: {
                 // modules.py:160-162  x_s = (conv1x1_out(y_{s-1}) + x_{s-1}) * sqrt(0.5)
                 const int j = idx + r;
                 if (j >= nx) break;
-                const float o = mine + bias[pl.bo_xb + s * pl.mx + j];
-                const float xp = (s == 1) ? x0own[j * BT + b] : xown[j * BT + b];
+                const float o = mine + bias_()[pl.bo_xb + s * pl.mx + j];
+                const float xp = (s == 1) ? x0own_()[j * BT + b] : xown_()[j * BT + b];
                 const float xn = (o + xp) * RSQRT2;
                 publish(ex, (long long)(pl.xoff + x0r + j) * BT + b, xn, tag);
-                xown[j * BT + b] = xn;
+                xown_()[j * BT + b] = xn;
             } break;
             case WN7_J_D: {
-                // older-tap products of layer s-1 -> history ring (consumed at steps t+d, t+2d, conv.py:32-44)
+                // older-tap products of layer s-1 -> history ring_() (consumed at steps t+d, t+2d, conv.py:32-44)
                 const int tap = idx / pl.my, i = idx % pl.my;
                 const int e = ((s - 1) * (pl.kw - 1) + tap) * 3;
-                ring[((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT + (2 * i + r) * BT + b] = mine;
+                ring_()[((size_t)ringtab_()[e] + ringtab_()[e + 2]) * RA4 * BT + (2 * i + r) * BT + b] = mine;
             } break;
             case WN7_J_S: {
                 // skip rows of layer s-1, accumulated in layer order (wavenet.py:312)
                 const int j = idx + r;
                 if (j >= ns) break;
-                const float h = mine + bias[pl.bo_sb + (s - 1) * pl.ms + j];
-                skipacc[j * BT + b] = (s == 1) ? h : skipacc[j * BT + b] + h;
+                const float h = mine + bias_()[pl.bo_sb + (s - 1) * pl.ms + j];
+                skipacc_()[j * BT + b] = (s == 1) ? h : skipacc_()[j * BT + b] + h;
             } break;
             case WN7_J_SL: {
                 // (s_0 + ... + s_{L-2}) + s_{L-1}, * sqrt(1/L), first ReLU of the head (wavenet.py:312-315)
                 const int j = idx + r;
                 if (j >= ns) break;
-                float tot = mine + bias[pl.bo_sb + (pl.L - 1) * pl.ms + j];
-                if (pl.L >= 2) tot = skipacc[j * BT + b] + tot;
+                float tot = mine + bias_()[pl.bo_sb + (pl.L - 1) * pl.ms + j];
+                if (pl.L >= 2) tot = skipacc_()[j * BT + b] + tot;
                 publish(ex, (long long)(s0 + j) * BT + b, fmaxf(tot * pl.skip_scale, 0.f), tag);
             } break;
             case WN7_J_HA: {
                 const int j = idx + r;
                 if (j >= na) break;
-                publish(ex, (long long)(a0 + j) * BT + b, fmaxf(mine + bias[pl.bo_ha + j], 0.f), tag);
+                publish(ex, (long long)(a0 + j) * BT + b, fmaxf(mine + bias_()[pl.bo_ha + j], 0.f), tag);
             } break;
             default: {   // WN7_J_HB
                 const int j = idx + r;
                 if (j >= nb) break;
-                publish(ex, (long long)(b0 + j) * BT + b, mine + bias[pl.bo_hb + j], tag);
+                publish(ex, (long long)(b0 + j) * BT + b, mine + bias_()[pl.bo_hb + j], tag);
             } break;
         }
-        (void)t;
     }
 
     __device__ void comp_loop() {
@@ -938,60 +943,78 @@ struct Engine {
         const bool prof = (pp.prof != nullptr) && cw == 0 && lane == 0;
         long long pc[4] = {0, 0, 0, 0}, tc = 0;
 #define WN7_TICK(i) if (prof) { const long long now_ = clock64(); pc[i] += now_ - tc; tc = now_; }
-        // skip-row passes per layer stage (all warps): the tail stage waits for all of them
+        // skip-row passes_() per layer stage (all warps): the tail stage waits for all of them
         int nskip = 0;
         for (int w = 0; w < WN7_NCW; ++w)
             for (int i = 0; i < pl.pass_count[WN7_K_LAYER][w]; ++i)
-                if (passes[pl.pass_begin[WN7_K_LAYER][w] + i].job == WN7_J_S) ++nskip;
+                if (passes_()[pl.pass_begin[WN7_K_LAYER][w] + i].job == WN7_J_S) ++nskip;
         uint32_t n = 0;
+        long long t_prev = clock64();
         const float* blob = nullptr;
         for (int t = 0; t < T && !dead; ++t) {
             if (prof) tc = clock64();
             for (int s = 0; s < NS; ++s, ++n) {
                 const int par = n & 1, kind = wn7_kind(pl, s);
                 if (s <= L) blob = acquire_blob(t, s);
-                if (s == 0) wait_bar(bar_pre, (uint32_t)t & 1u, 0x02000000u);          // pre-sums of this step are built
-                if (s == 1) wait_bar(bar_x0, (uint32_t)t & 1u, 0x02000001u);           // x_0 at the owned rows is in place
+                if (s == 0) wait_bar(bar_pre_(), (uint32_t)t & 1u, 0x02000000u);          // pre_()-sums of this step are built
+                if (s == 1) wait_bar(bar_x0_(), (uint32_t)t & 1u, 0x02000001u);           // x_0 at the owned rows is in place
                 const int begin = pl.pass_begin[kind][cw], cnt = pl.pass_count[kind][cw], crit = pl.pass_crit[kind][cw];
-                float4 pwa[WPRE], pwb[WPRE];
-                if (cnt > 0 && !dead) preload_pass(passes[begin], blob, pwa, pwb);
-                WN7_TICK(0);
-                if (!wait_bar(&bar_in[par], (n >> 1) & 1u, 0x08000000u | (uint32_t)s)) break;
-                WN7_TICK(1);
-                const float* xb = xin + (size_t)par * xin_floats;
-                bool had_skip = false;
-                for (int i = 0; i < cnt; ++i) {
-                    const Wn7Pass& ps = passes[begin + i];
-                    if (ps.job == WN7_J_SL && L >= 2) {
-                        // skip rows of layers 0..L-2 are accumulated by the deferred passes of stages 1..L-1
-                        wait_count(s_skipcnt, (t * (L - 1) + (L - 1)) * nskip, 0x02000002u);
-                        if (dead) break;
+                float* xb = xin_() + (size_t)par * xin_floats;
+                const bool i_poll = SELF && cw < WN7_NSP;
+                if (i_poll) {
+                    // this warp is one of the pollers: the buffer must be free, then the rare heavy part of the duty
+                    if (n >= 2) {
+                        if (!wait_bar(&bar_free_()[par], ((n >> 1) - 1) & 1u, 0x10000000u | (uint32_t)s)) break;
                     }
-                    if (i == 0) run_pass<true>(ps, blob, xb, s, t, n + 1u, pwa, pwb);
-                    else run_pass<false>(ps, blob, xb, s, t, n + 1u, pwa, pwb);
-                    if (ps.job == WN7_J_S) had_skip = true;
+                    poll_stage_head(t, s, xb, cw * 32 + lane, 32 * WN7_NSP);
+                    if (dead) break;
+                }
+                WN7_TICK(0);
+                if (i_poll) {
+                    if (pl.gate_cycles > 0) { while (clock64() - t_prev < pl.gate_cycles) {} }
+                    poll_stage_loads(s, n, xb, cw * 32 + lane, 32 * WN7_NSP);     // its share of the vector ...
+                    poller_sync();                                                // ... then the group barrier
+                    if (dead) break;
+                    if (lane == 0) mbar_arrive(&bar_in_()[par]);     // releases the compute warps that do not poll
+                    t_prev = clock64();
+                } else {
+                    if (!wait_bar(&bar_in_()[par], (n >> 1) & 1u, 0x08000000u | (uint32_t)s)) break;
+                }
+                WN7_TICK(1);
+                bool had_skip = false;
+                if (kind == WN7_K_TAIL && L >= 2) {
+                    // skip rows of layers 0..L-2 are accumulated by the deferred passes_() of stages 1..L-1
+                    bool need = false;
+                    for (int i = 0; i < cnt; ++i) need |= passes_()[begin + i].job == WN7_J_SL;
+                    if (need) wait_count(s_skipcnt_(), (t * (L - 1) + (L - 1)) * nskip, 0x02000002u);
+                    if (dead) break;
+                }
+                for (int i = 0; i < cnt; ++i) {
+                    const Wn7Pass& ps = passes_()[begin + i];
+                    run_pass(ps, blob, xb, s, n + 1u);
+                    had_skip |= ps.job == WN7_J_S;
                     if (i + 1 == crit) WN7_TICK(2);
                 }
-                if (dead) break;
                 __syncwarp();
                 if (had_skip) {
                     __threadfence_block();
                     if (lane == 0) {
                         int c = 0;
-                        for (int i = 0; i < cnt; ++i) c += passes[begin + i].job == WN7_J_S;
-                        atomicAdd((int*)s_skipcnt, c);
+                        for (int i = 0; i < cnt; ++i) c += passes_()[begin + i].job == WN7_J_S;
+                        atomicAdd((int*)s_skipcnt_(), c);
                     }
                 }
-                if (lane == 0) mbar_arrive(&bar_free[par]);
+                if (lane == 0) mbar_arrive(&bar_free_()[par]);
                 if (s < L || s == NS - 1) release_blob(wn7_blob_of_stage(pl, s));
                 if (s == L) {
-                    // every deferred product of this step is in its ring: HK may advance the rings and build the next table
+                    // every deferred product of this step is in its ring_(): HK may advance the rings and build the next table
                     __threadfence_block();
-                    if (lane == 0) mbar_arrive(bar_dstep);
+                    if (lane == 0) mbar_arrive(bar_dstep_());
                 }
                 WN7_TICK(3);
             }
         }
+        if (SELF && cw < WN7_NSP && !dead) read_head_and_sample(T - 1, cw * 32 + lane, 32 * WN7_NSP);
         if (prof) {
             for (int i = 0; i < 4; ++i) pp.prof[(size_t)p * 16 + 8 + i] = pc[i];
         }
@@ -999,40 +1022,40 @@ struct Engine {
     }
 
     // ======================================================================================
-    // housekeeping warp: ring positions and the pre-sum table, once per step
+    // housekeeping warp: ring_() positions and the pre_()-sum table, once per step
     // ======================================================================================
-    // Everything of z_l(t) that does not depend on step t's exchanges: (folded) bias + global conditioning +
+    // Everything of z_l(t) that does not depend on step t's exchanges: (folded) bias_() + global conditioning +
     // local-conditioning projection + the queued products of the older taps.
     __device__ void build_pre(int t) {
         const int L = pl.L, RA4 = 4 * pl.qA, kw = pl.kw, n = L * RA4 * BT;
-        if (pl.C > 0) wait_bar<true>(&bar_cfull[t & 1], (uint32_t)(t >> 1) & 1u, 0x01000000u);
+        if (pl.C > 0) wait_bar<true>(&bar_cfull_()[t & 1], (uint32_t)(t >> 1) & 1u, 0x01000000u);
         if (dead) return;
-        const float* cd = cond + (size_t)(t & 1) * L * RA4 * BT;
+        const float* cd = cond_() + (size_t)(t & 1) * L * RA4 * BT;
         for (int i = lane; i < n; i += 32) {
             const int l = i / (RA4 * BT), rem = i % (RA4 * BT);
-            float v = sb[i];
+            float v = sb_()[i];
             if (pl.C > 0) v += cd[i];
             for (int k = 0; k < kw - 1; ++k) {
                 const int e = (l * (kw - 1) + k) * 3;
-                v += ring[((size_t)ringtab[e] + ringtab[e + 2]) * RA4 * BT + rem];
+                v += ring_()[((size_t)ringtab_()[e] + ringtab_()[e + 2]) * RA4 * BT + rem];
             }
-            pre[i] = v;
+            pre_()[i] = v;
         }
         __syncwarp();
         if (lane == 0) {
-            if (pl.C > 0) mbar_arrive(&bar_cempty[t & 1]);
-            mbar_arrive(bar_pre);
+            if (pl.C > 0) mbar_arrive(&bar_cempty_()[t & 1]);
+            mbar_arrive(bar_pre_());
         }
     }
     __device__ void hk_loop() {
         const int L = pl.L, T = pp.T, kw = pl.kw;
         build_pre(0);
         for (int t = 0; t < T && !dead; ++t) {
-            if (!wait_bar<true>(bar_dstep, (uint32_t)t & 1u, 0x00800000u)) break;
-            // advance the ring positions to (t+1) mod delay, then the pre-sums of step t+1
+            if (!wait_bar<true>(bar_dstep_(), (uint32_t)t & 1u, 0x00800000u)) break;
+            // advance the ring_() positions to (t+1) mod delay, then the pre_()-sums of step t+1
             for (int i = lane; i < L * (kw - 1); i += 32) {
-                const int pos = ringtab[i * 3 + 2] + 1;
-                ringtab[i * 3 + 2] = (pos == ringtab[i * 3 + 1]) ? 0 : pos;
+                const int pos = ringtab_()[i * 3 + 2] + 1;
+                ringtab_()[i * 3 + 2] = (pos == ringtab_()[i * 3 + 1]) ? 0 : pos;
             }
             __threadfence_block();
             __syncwarp();
@@ -1044,61 +1067,62 @@ struct Engine {
 // ------------------------------------------------------------------------------------------
 // kernel entry
 // ------------------------------------------------------------------------------------------
-template <int BT>
-__global__ void __launch_bounds__(32 * (WN7_MAX_NPW + WN7_NCW + 3), 1)
+template <int BT, bool SELF>
+__global__ void __launch_bounds__(32 * ((SELF ? 0 : WN7_MAX_NPW) + WN7_NCW + 3), 1)
 wn7_kernel(const __grid_constant__ Wn7Plan pl, const __grid_constant__ Wn7Ptrs pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Engine<BT> eng(pl, pp, smem_raw);
+    Engine<BT, SELF> eng(pl, pp, smem_raw);
+    const int npollw = SELF ? WN7_NSP : pl.npw;
     const int tid = threadIdx.x, p = blockIdx.x, warp = tid >> 5, NT = pl.nthreads;
     const int nslots = pl.nres + pl.nring;
     const int L = pl.L, RA4 = 4 * pl.qA;
     if (tid == 0) {
-        for (int i = 0; i < nslots; ++i) mbar_init(&eng.bar_full[i], 1);
-        for (int i = 0; i < pl.nring; ++i) mbar_init(&eng.bar_empty[i], WN7_NCW);
+        for (int i = 0; i < nslots; ++i) mbar_init(&eng.bar_full_()[i], 1);
+        for (int i = 0; i < pl.nring; ++i) mbar_init(&eng.bar_empty_()[i], WN7_NCW);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&eng.bar_cfull[i], 1);
-            mbar_init(&eng.bar_cempty[i], 1);
-            mbar_init(&eng.bar_in[i], pl.npw);
-            mbar_init(&eng.bar_free[i], WN7_NCW);
+            mbar_init(&eng.bar_cfull_()[i], 1);
+            mbar_init(&eng.bar_cempty_()[i], 1);
+            mbar_init(&eng.bar_in_()[i], npollw);
+            mbar_init(&eng.bar_free_()[i], WN7_NCW);
         }
-        mbar_init(eng.bar_pre, 1);
-        mbar_init(eng.bar_x0, pl.npw);
-        mbar_init(eng.bar_ps, pl.npw);
-        mbar_init(eng.bar_dstep, WN7_NCW);
-        *eng.s_abort = 0;
-        *eng.s_skipcnt = 0;
+        mbar_init(eng.bar_pre_(), 1);
+        mbar_init(eng.bar_x0_(), npollw);
+        mbar_init(eng.bar_ps_(), npollw);
+        mbar_init(eng.bar_dstep_(), WN7_NCW);
+        *eng.s_abort_() = 0;
+        *eng.s_skipcnt_() = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // pass table
     {
         const int nw = pl.npass * (int)(sizeof(Wn7Pass) / 4);
         const int* src = reinterpret_cast<const int*>(pp.passes);
-        int* dst = reinterpret_cast<int*>(eng.passes);
+        int* dst = reinterpret_cast<int*>(eng.passes_());
         for (int i = tid; i < nw; i += NT) dst[i] = src[i];
     }
     // zero the history (== the reference's zero-initialised queue, conv.py:35-36) and the scratch buffers
     if (pl.ring_in_smem) {
         const size_t n = (size_t)pl.ring_pos_total * RA4 * BT;
-        for (size_t i = tid; i < n; i += NT) eng.ring[i] = 0.f;
+        for (size_t i = tid; i < n; i += NT) eng.ring_()[i] = 0.f;
     }
-    for (int i = tid; i < 2 * pl.xin_vals * BT; i += NT) eng.xin[i] = 0.f;
-    for (int i = tid; i < pl.ms * BT; i += NT) eng.skipacc[i] = 0.f;
-    for (int i = tid; i < 2 * pl.mx * BT; i += NT) eng.xown[i] = 0.f;
-    for (int i = tid; i < pl.O * BT + 2; i += NT) eng.hs[i] = 0.f;
+    for (int i = tid; i < 2 * pl.xin_vals * BT; i += NT) eng.xin_()[i] = 0.f;
+    for (int i = tid; i < pl.ms * BT; i += NT) eng.skipacc_()[i] = 0.f;
+    for (int i = tid; i < 2 * pl.mx * BT; i += NT) eng.xown_()[i] = 0.f;
+    for (int i = tid; i < pl.O * BT + 2; i += NT) eng.hs_()[i] = 0.f;
     for (int i = tid; i < pl.L * (pl.kw - 1); i += NT) {
-        eng.ringtab[i * 3] = pp.ringtab[i * 2];           // offset of the ring (in positions)
-        eng.ringtab[i * 3 + 1] = pp.ringtab[i * 2 + 1];   // delay D
-        eng.ringtab[i * 3 + 2] = 0;                       // t mod D
+        eng.ringtab_()[i * 3] = pp.ringtab[i * 2];           // offset of the ring (in positions)
+        eng.ringtab_()[i * 3 + 1] = pp.ringtab[i * 2 + 1];   // delay D
+        eng.ringtab_()[i * 3 + 2] = 0;                       // t mod D
     }
     // biases of the rows this block owns
     {
         const float* src = pp.bpack + (size_t)p * pl.cta_b_floats;
-        for (int i = tid; i < pl.cta_b_floats; i += NT) eng.bias[i] = src[i];
+        for (int i = tid; i < pl.cta_b_floats; i += NT) eng.bias_()[i] = src[i];
     }
     // first 1x1 conv: [w (scalar input) | b]
     for (int k = tid; k < pl.R; k += NT) {
-        eng.x0w[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
-        eng.x0w[pl.R + k] = pp.first_b[k];
+        eng.x0w_()[k] = (pl.input_kind == 0) ? pp.first_w[k] : 0.f;
+        eng.x0w_()[pl.R + k] = pp.first_b[k];
     }
     {
         // static part of the pre-activation: (folded) conv bias + global-conditioning projection
@@ -1115,7 +1139,7 @@ wn7_kernel(const __grid_constant__ Wn7Plan pl, const __grid_constant__ Wn7Ptrs p
                     v += pp.gbias[((size_t)b * L + l) * pl.G + grow];
                 }
             }
-            eng.sb[i] = v;
+            eng.sb_()[i] = v;
         }
     }
     // feedback for step 0 (wavenet.py:281-301)
@@ -1134,8 +1158,8 @@ wn7_kernel(const __grid_constant__ Wn7Plan pl, const __grid_constant__ Wn7Ptrs p
                 else idx = pp.initial_index;
             }
         } else if (pl.input_kind != 0) idx = 0;
-        eng.s_in[b] = v;
-        eng.s_idx[b] = idx;
+        eng.s_in_()[b] = v;
+        eng.s_idx_()[b] = idx;
     }
     if (pl.input_kind != 0) {
         const float* dsrc = nullptr;
@@ -1144,11 +1168,11 @@ wn7_kernel(const __grid_constant__ Wn7Plan pl, const __grid_constant__ Wn7Ptrs p
         else if (pp.T_test == 0 && pp.initial_dense != nullptr) { dsrc = pp.initial_dense; stride = (size_t)pl.O; }
         for (int i = tid; i < BT * pl.O; i += NT) {
             const int b = i / pl.O, o = i % pl.O;
-            eng.s_dense[i] = (dsrc && b < pp.B) ? dsrc[(size_t)b * stride + o] : 0.f;
+            eng.s_dense_()[i] = (dsrc && b < pp.B) ? dsrc[(size_t)b * stride + o] : 0.f;
         }
     }
-    if (warp < pl.npw) {
-        for (int b = warp; b < BT; b += pl.npw) eng.fetch_noise(0, b);
+    if (warp < npollw) {
+        for (int b = warp; b < BT; b += npollw) eng.fetch_noise(0, b);
     }
     __syncthreads();
 

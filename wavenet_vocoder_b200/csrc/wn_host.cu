@@ -438,7 +438,7 @@ struct WnHandle {
     std::vector<Wn7Pass> passes7;
     float* d_bpack = nullptr;
     Wn7Pass* d_passes = nullptr;
-    bool attr7_set[4] = {};
+    bool attr7_set[8] = {};
     // local-conditioning upsampler (wn_load_upsampler)
     bool have_ups = false;
     wnaux::UpsampleDesc ups;
@@ -678,19 +678,27 @@ static int32_t run_upsampler(WnHandle* h, const float* c_frames, int B, int F, i
     return WN_OK;
 }
 
-static const void* kernel7_for(int BT) {
+static const void* kernel7_for(int BT, bool self) {
+    if (self) {
+        switch (BT) {
+            case 1: return (const void*)wn7::wn7_kernel<1, true>;
+            case 2: return (const void*)wn7::wn7_kernel<2, true>;
+            case 4: return (const void*)wn7::wn7_kernel<4, true>;
+            default: return (const void*)wn7::wn7_kernel<8, true>;
+        }
+    }
     switch (BT) {
-        case 1: return (const void*)wn7::wn7_kernel<1>;
-        case 2: return (const void*)wn7::wn7_kernel<2>;
-        case 4: return (const void*)wn7::wn7_kernel<4>;
-        default: return (const void*)wn7::wn7_kernel<8>;
+        case 1: return (const void*)wn7::wn7_kernel<1, false>;
+        case 2: return (const void*)wn7::wn7_kernel<2, false>;
+        case 4: return (const void*)wn7::wn7_kernel<4, false>;
+        default: return (const void*)wn7::wn7_kernel<8, false>;
     }
 }
 
-static int32_t prepare_kernel7(WnHandle* h, int BT) {
-    const int ai = bt_index(BT);
+static int32_t prepare_kernel7(WnHandle* h, int BT, bool self) {
+    const int ai = bt_index(BT) + (self ? 4 : 0);
     if (h->attr7_set[ai]) return WN_OK;
-    const void* fn = kernel7_for(BT);
+    const void* fn = kernel7_for(BT, self);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
     h->attr7_set[ai] = true;
     return WN_OK;
@@ -774,7 +782,7 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
         CUDA_TRY(cudaMemsetAsync(h->d_prof, 0, pb, st));
         pp.prof = h->d_prof;
     }
-    rc = prepare_kernel7(h, BT);
+    rc = prepare_kernel7(h, BT, pl.npw == 0);
     if (rc) return rc;
     void* kargs[2] = {(void*)&pl, (void*)&pp};
     // cooperative launch: the runtime refuses to start unless all P blocks are co-resident, which the
@@ -790,7 +798,7 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
     la[0].val.cooperative = 1;
     lc.attrs = la;
     lc.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelExC(&lc, kernel7_for(BT), kargs));
+    CUDA_TRY(cudaLaunchKernelExC(&lc, kernel7_for(BT, pl.npw == 0), kargs));
     h->launches++;
     return WN_OK;
 }
@@ -926,7 +934,7 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
     // freeze the partition so every batch tile agrees with the packing
     if (h->engine == 7) {
         h->cfg.num_ctas = h->base7.P;
-        h->cfg.poll_warps = h->base7.npw;
+        h->cfg.poll_warps = h->base7.npw == 0 ? -1 : h->base7.npw;
     } else {
         h->cfg.num_ctas = h->base.P;
         h->cfg.exchange_copies = h->base.ncopy;
