@@ -198,7 +198,7 @@ static int32_t build_plan7(const wn_config& c, int batch, int num_sms, long long
             return (int)r;
         };
         const long long tab = (long long)pl.L * 4 * pl.qA * BT * 4;
-        pl.sm_bar = take((long long)(2 * pl.nblobs + 16) * 8, 16);
+        pl.sm_bar = take((long long)(2 * pl.nblobs + 20) * 8, 16);
         pl.sm_misc = take(16, 16);
         pl.sm_in = take((long long)BT * 8 + (pl.input_kind == WN_INPUT_ONEHOT ? (long long)BT * pl.O * 4 : 0), 16);
         pl.sm_pass = take((long long)pl.npass * (long long)sizeof(Wn7Pass), 16);

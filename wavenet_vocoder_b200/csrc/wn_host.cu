@@ -549,6 +549,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.noise_kind = a->noise_kind;
     pp.seed = a->seed;
     pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
+    pp.warp_reverse = env_int("WN_WARP_REVERSE", 1);
     pp.prof = nullptr;
     if (env_int("WN_PROF", 0)) {
         const size_t pb = (size_t)pl.P * 16 * sizeof(long long);
@@ -742,6 +743,8 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
     pp.cwpack = h->d_cwpack;
     pp.bpack = h->d_bpack;
     pp.passes = h->d_passes;
+    pp.warp_reverse = env_int("WN_WARP_REVERSE", 1);
+    pp.defer_gate = env_int("WN_DEFER_GATE", 1);
     pp.first_w = h->d_first_w;
     pp.first_b = h->d_first_b;
     pp.xbuf = h->d_xbuf;

@@ -85,6 +85,7 @@ struct WnPtrs {
     unsigned long long seed;
     long long timeout_cycles;
     long long* prof;           // optional [P][8] cycle counters (scripts/sweep.py --prof)
+    int warp_reverse;          // 1: logical warp = 9 - physical warp (the issue arbiter favours high warp ids)
 };
 
 #define WN_FLAG_SOFTMAX_ 1u
@@ -310,9 +311,11 @@ struct Engine {
 
     __device__ Engine(const WnPlan& pl_, const WnPtrs& pp_, unsigned char* sm_)
         : pl(pl_), pp(pp_), sm(sm_) {
-        tid = threadIdx.x;
-        warp = tid >> 5;
-        lane = tid & 31;
+        // logical thread index: the SM's issue arbiter prefers the highest warp id among eligible warps, so the
+        // critical group (logical warps 0-3) is mapped onto the highest physical warps when warp_reverse is set
+        lane = threadIdx.x & 31;
+        warp = pp.warp_reverse ? (WN_NTHREADS / 32 - 1) - (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5);
+        tid = warp * 32 + lane;
         p = blockIdx.x;
         gt = tid & (WN_NTC - 1);
         gw = warp & (WN_GW - 1);
@@ -1223,7 +1226,7 @@ __global__ void __launch_bounds__(WN_NTHREADS, 1)
 wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ WnPtrs pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Engine<BT, ER, EG> eng(pl, pp, smem_raw);
-    const int tid = threadIdx.x, p = blockIdx.x;
+    const int tid = eng.tid, p = blockIdx.x;      // logical thread index (see Engine)
     const int nslots = pl.nres + pl.nring;
     if (tid == 0) {
         for (int i = 0; i < nslots; ++i) mbar_init(&eng.bar_full[i], 1);
