@@ -464,7 +464,8 @@ struct WnHandle {
     bool pending = false;
     int64_t launches = 0;
     bool attr_set[16] = {};
-    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 carve-out for the packed weights
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 carve-out
+    int l2_mode = 0;                                  // WN_L2_PERSIST: 1 = packed weights, 2 = exchange buffer
     size_t wpack_bytes = 0;
 };
 
@@ -549,7 +550,8 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.noise_kind = a->noise_kind;
     pp.seed = a->seed;
     pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
-    pp.warp_reverse = env_int("WN_WARP_REVERSE", 1);
+    pp.warp_reverse = env_int("WN_WARP_REVERSE", 0);
+    pp.gate_cycles = env_int("WN_GATE_CYCLES", 0);
     pp.prof = nullptr;
     if (env_int("WN_PROF", 0)) {
         const size_t pb = (size_t)pl.P * 16 * sizeof(long long);
@@ -595,7 +597,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     la[na].id = cudaLaunchAttributeCooperative;
     la[na].val.cooperative = 1;
     ++na;
-    if (h->l2_persist_bytes > 0 && h->wpack_bytes > 0) {
+    if (h->l2_mode == 1 && h->l2_persist_bytes > 0 && h->wpack_bytes > 0) {
         const size_t win = std::min(h->wpack_bytes, h->l2_window_max);
         la[na].id = cudaLaunchAttributeAccessPolicyWindow;
         la[na].val.accessPolicyWindow.base_ptr = (void*)h->d_wpack;
@@ -603,6 +605,16 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
         la[na].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_bytes / (double)win);
         la[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         la[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    } else if (h->l2_mode == 2 && h->l2_persist_bytes > 0) {
+        // keep the exchange buffer (a few MB, every line touched once per generated sample) in the persisting part of
+        // L2: the 112 MB/sample weight stream otherwise evicts it between two steps
+        la[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        la[na].val.accessPolicyWindow.base_ptr = (void*)h->d_xbuf;
+        la[na].val.accessPolicyWindow.num_bytes = std::min(xb, h->l2_window_max);
+        la[na].val.accessPolicyWindow.hitRatio = 1.0f;
+        la[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        la[na].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
         ++na;
     }
     lc.attrs = la;
@@ -796,11 +808,22 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
     lc.blockDim = dim3(pl.nthreads);
     lc.dynamicSmemBytes = (size_t)pl.smem_bytes;
     lc.stream = st;
-    cudaLaunchAttribute la[1];
-    la[0].id = cudaLaunchAttributeCooperative;
-    la[0].val.cooperative = 1;
+    cudaLaunchAttribute la[2];
+    int na = 0;
+    la[na].id = cudaLaunchAttributeCooperative;
+    la[na].val.cooperative = 1;
+    ++na;
+    if (h->l2_mode == 2 && h->l2_persist_bytes > 0) {
+        la[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        la[na].val.accessPolicyWindow.base_ptr = (void*)h->d_xbuf;
+        la[na].val.accessPolicyWindow.num_bytes = std::min(xb, h->l2_window_max);
+        la[na].val.accessPolicyWindow.hitRatio = 1.0f;
+        la[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        la[na].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        ++na;
+    }
     lc.attrs = la;
-    lc.numAttrs = 1;
+    lc.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelExC(&lc, kernel7_for(BT, pl.npw == 0), kargs));
     h->launches++;
     return WN_OK;
@@ -924,10 +947,13 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
         delete h;
         return rc;
     }
-    if (h->engine == 5 && env_int("WN_L2_PERSIST", 0) && prop.persistingL2CacheMaxSize > 0) {
-        // Optional (WN_L2_PERSIST=1): pin as much of the packed weight image as allowed in the persisting part of
-        // the 126 MB L2.  Measured 44.7 us/sample with the window vs 44.1 without, so off.
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+    h->l2_mode = env_int("WN_L2_PERSIST", 0);
+    if (h->l2_mode > 0 && prop.persistingL2CacheMaxSize > 0) {
+        // Optional: WN_L2_PERSIST=1 pins as much of the packed weight image as allowed in the persisting part of the
+        // 126 MB L2 (measured 44.7 us/sample with the window vs 44.1 without); =2 pins the exchange buffer instead.
+        const size_t want = h->l2_mode == 2 ? std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 16u << 20)
+                                             : (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             h->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
             h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
         } else {
