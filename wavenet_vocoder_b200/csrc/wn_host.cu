@@ -425,8 +425,11 @@ static int32_t check_weights(const wn_config& c, const wn_weights* w) {
 
 #include "wn7_host.cuh"
 
-// which kernel generation: 7 = polling warps + warp-per-row-pair passes (default), 5 = the round-1 kernel
-static int engine_choice() { return env_int("WN_ENGINE", 7) == 5 ? 5 : 7; }
+// which kernel organisation: 5 (default) = critical / deferred warp groups, values polled straight into the registers
+// of the threads that use them, quad-major GEMV + butterfly + one group barrier (csrc/wn_kernel.cuh); 7 = the round-2
+// alternative: row-pair passes finalised inside the warp, up to 8 utterances per launch (csrc/wn7_kernel.cuh).
+// Both are parity-tested; measured on a B200 (profiles/r2_*): 44 us vs 100-112 us per sample for config 2.
+static int engine_choice() { return env_int("WN_ENGINE", 5) == 7 ? 7 : 5; }
 
 // ------------------------------------------------------------------------------------------
 // handle
@@ -528,6 +531,8 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.err = h->d_err;
     pp.c = a->c ? a->c + (size_t)b0 * T * pl.C : nullptr;
     pp.initial = a->initial ? a->initial + b0 : nullptr;
+    pp.initial_dense = a->initial_dense ? a->initial_dense + (size_t)b0 * O : nullptr;
+    pp.initial_rows = a->initial_rows ? a->initial_rows + b0 : nullptr;
     pp.test_scalar = a->test_scalar ? a->test_scalar + (size_t)b0 * Tt : nullptr;
     pp.test_index = a->test_index ? a->test_index + (size_t)b0 * Tt : nullptr;
     pp.test_dense = a->test_dense ? a->test_dense + (size_t)b0 * Tt * O : nullptr;
@@ -1099,8 +1104,6 @@ static int32_t validate_args(const WnHandle* h, const wn_generate_args* a) {
         const int start = a->initial_index < 0 ? 127 : a->initial_index;
         if (a->T_test == 0 && !a->initial_rows && !a->initial_dense && start >= c.out_channels)
             return fail(WN_ERR_INVALID, "initial_index out of range (the default start class is 127, wavenet.py:286)");
-        if ((a->initial_rows || a->initial_dense) && h->engine != 7)
-            return fail(WN_ERR_INVALID, "per-utterance initial inputs need the default engine");
     }
     if (a->noise_kind == WN_NOISE_REPLAY) {
         const bool quant = (a->flags & WN_FLAG_QUANTIZE) != 0;

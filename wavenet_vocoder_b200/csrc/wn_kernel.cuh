@@ -68,6 +68,8 @@ struct WnPtrs {
     // ---- per call
     const float* c;
     const float* initial;
+    const float* initial_dense;   // one-hot input: (B,O) dense start vector or NULL
+    const int* initial_rows;      // one-hot input: (B) start class per utterance or NULL
     const float* test_scalar;
     const int* test_index;
     const float* test_dense;
@@ -833,7 +835,7 @@ struct Engine {
                 } else {
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
-                        const int idx = s_idx[b];
+                        const int idx = min(s_idx[b], O - 1);      // class ids are range-checked on the host where it can
                         if (idx >= 0) {
                             // one-hot input: the GEMV is a column gather
                             x[j][b] = __ldg(pp.first_w + (size_t)idx * R + k) + first[R + k];
@@ -1291,16 +1293,22 @@ wn_persistent_kernel(const __grid_constant__ WnPlan pl, const __grid_constant__ 
                 else if (pp.initial) v = pp.initial[b];
             } else {
                 if (pp.T_test > 0) idx = pp.test_index ? pp.test_index[(size_t)b * pp.T_test] : -1;
+                else if (pp.initial_dense) idx = -1;
+                else if (pp.initial_rows) idx = pp.initial_rows[b];
                 else idx = pp.initial_index;
             }
         } else if (pl.input_kind != 0) idx = 0;
         eng.s_in[b] = v;
         eng.s_idx[b] = idx;
     }
-    if (pl.input_kind != 0 && pp.T_test > 0 && pp.test_dense != nullptr) {
+    if (pl.input_kind != 0) {
+        const float* dsrc = nullptr;
+        size_t stride = 0;
+        if (pp.T_test > 0 && pp.test_dense != nullptr) { dsrc = pp.test_dense; stride = (size_t)pp.T_test * pl.O; }
+        else if (pp.T_test == 0 && pp.initial_dense != nullptr) { dsrc = pp.initial_dense; stride = (size_t)pl.O; }
         for (int i = tid; i < BT * pl.O; i += WN_NTHREADS) {
             const int b = i / pl.O, o = i % pl.O;
-            eng.s_dense[i] = (b < pp.B) ? pp.test_dense[((size_t)b * pp.T_test) * pl.O + o] : 0.f;
+            eng.s_dense[i] = (dsrc && b < pp.B) ? dsrc[(size_t)b * stride + o] : 0.f;
         }
     }
     const int warp = tid >> 5;
