@@ -328,22 +328,31 @@ def main():
         U4, K4 = 8, max(1, min(K, 3))
         c4 = c_dev[:1].expand(U4, -1, -1).contiguous() if U < U4 else c_dev[:U4]
         c4 = c4 + 0.01 * torch.randn(c4.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+        conc = hasattr(eng, "generate_concurrent") and eng.plan(1)["engine"] == 5 and os.environ.get("WN_CONCURRENT_TILES", "1") != "0"
+
+        def step4(seed, sync):
+            if conc:      # two tiles of 4 at the same time on two half-grid engines (engine.generate_concurrent)
+                return eng.generate_concurrent(B=U4, T=T, c=c4, seed=seed, sync=sync)
+            return eng.generate(B=U4, T=T, c=c4, seed=seed, sync=sync)[0]
         for i in range(2):
-            eng.generate(B=U4, T=T, c=c4, seed=100 + i, sync=True)
+            step4(100 + i, True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for i in range(K4):
-            eng.generate(B=U4, T=T, c=c4, seed=200 + i, sync=False)
+            step4(200 + i, False)
         e1.record()
         barrier()
+        if conc:
+            eng.sync_concurrent()
         t4 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t4, op=dist.ReduceOp.MAX)
         sps4 = U4 * T * K4 * world / (float(t4.item()) * 1e-3)
         peak4, _ = measured_peak()
         roof4 = U4 * peak4 * 1e9 / plan["weight_bytes_per_step"]          # samples/s per GPU if the weights stream at peak
-        cfg4 = {"workload": "BASELINE config 4 share: %d utterances per GPU, T=%d, one launch" % (U4, T),
+        cfg4 = {"workload": "BASELINE config 4 share: %d utterances per GPU, T=%d, %s" % (
+                    U4, T, "two tiles of 4 at the same time on two half-grid engines" if conc else "tiles of <= %d, one after the other" % eng.plan(U4)["batch_tile"]),
                 "value": sps4, "unit": "samples/s", "per_gpu": sps4 / world, "steps": K4,
                 "ms_per_step": float(t4.item()) / K4, "batch_tile": eng.plan(U4)["batch_tile"],
                 "frac_of_weight_roof": (sps4 / world) / roof4, "weight_roof_samples_per_s_per_gpu": roof4}

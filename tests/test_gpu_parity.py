@@ -739,3 +739,24 @@ def test_config2_full_length_strided_oracle():
 def test_config5_long_form_strided_oracle():
     """BASELINE config 5: T = 240 000 (10 s at 24 kHz): tag arithmetic, 234 wraps of the largest history ring."""
     strided_oracle_check("cfg5_mol30", 240000, [0, 239000], 192, 2e-5 * 2.5)
+
+
+def test_concurrent_half_grid_tiles_equal_sequential_tiles():
+    """BASELINE config 4's per-GPU share (8 utterances) as two batch tiles of 4 running at the same time on two
+    half-grid engines: every tile must equal the same tile run alone on the full grid with the same seed (the row
+    partition only changes the fp32 summation order)."""
+    m, cfg, w, _ = full_case("cfg2_mol24")
+    mc = m.cuda()
+    eng = mc._get_engine()
+    if eng.plan(1)["engine"] != 5:
+        pytest.skip("the concurrent-tile path is built on the default engine")
+    B, T = 8, 48
+    gen = torch.Generator().manual_seed(12)
+    c = torch.randn(B, T, cfg.cin_channels, generator=gen).cuda()
+    out = eng.generate_concurrent(B=B, T=T, c=c, seed=99)
+    assert tuple(out.shape) == (B, T) and bool(torch.isfinite(out).all())
+    for k, b0 in enumerate(range(0, B, 4)):
+        ref, _ = eng.generate(B=4, T=T, c=c[b0:b0 + 4].contiguous(), seed=99 + k)
+        rms = float(((out[b0:b0 + 4] - ref) ** 2).mean().sqrt())
+        assert rms <= RMS_TOL, (k, rms)
+    assert not torch.equal(out[:4], out[4:])

@@ -126,8 +126,18 @@ class SynthesisEngine:
         self._h = C.c_void_p()
         N.check(N.lib().wn_create(C.byref(cfg), C.byref(self._h)))
         self._keep = None
+        self._ctor = dict(layers=layers, stacks=stacks, residual_channels=residual_channels, gate_channels=gate_channels,
+                          skip_out_channels=skip_out_channels, out_channels=out_channels, kernel_size=kernel_size,
+                          cin_channels=cin_channels, gin_channels=gin_channels, scalar_input=scalar_input,
+                          output_distribution=output_distribution, device=device)
+        self._sd = None
+        self._halves = None           # two half-grid engines for concurrent batch tiles (see generate_concurrent)
+        self._is_child = num_ctas > 0
 
     def close(self):
+        for ch in (getattr(self, "_halves", None) or []):
+            ch["eng"].close()
+        self._halves = None
         if getattr(self, "_h", None) is not None and self._h.value:
             N.lib().wn_destroy(self._h)
             self._h = C.c_void_p()
@@ -144,6 +154,11 @@ class SynthesisEngine:
         w, keep = weights_struct(sd, self.cfg.layers, self.cin, self.gin)
         N.check(N.lib().wn_load_weights(self._h, C.byref(w)))
         del keep
+        if not self._is_child:
+            self._sd = {k: v.detach().cpu() for k, v in sd.items() if not k.startswith("upsample_net.")}
+            for ch in (self._halves or []):
+                ch["eng"].close()
+            self._halves = None
 
     def load_upsampler(self, net) -> bool:
         """Hand the local-conditioning upsampler (upsample.py:29-85 there) to libwn so that ``generate`` can take
@@ -301,6 +316,59 @@ class SynthesisEngine:
         if sync:
             self.sync()
         return out, params
+
+    # ------------------------------------------------------------------ two batch tiles at a time
+    def generate_concurrent(self, *, B: int, T: int, c: Optional[torch.Tensor] = None, g: Optional[torch.Tensor] = None,
+                            seed: Optional[int] = None, sync=True):
+        """Free-running synthesis of B > one tile of utterances with device-drawn noise: two HALF-GRID engines (64
+        blocks each) run two batch tiles at the same time on two streams, instead of one full-grid launch per tile one
+        after the other (BASELINE config 4's per-GPU share of 8 utterances is two tiles of 4).  A step of the sample
+        loop is latency-bound, not SM-bound, so two half-grid chains overlap almost perfectly.  Utterances are independent;
+        tile k draws its noise from seed + k.  Returns (B,T) samples (scalar-input models)."""
+        if not self.scalar_input:
+            raise ValueError("generate_concurrent supports scalar-input models")
+        plan = self.plan(1)
+        half = max(1, plan["num_ctas"] // 2)
+        tile = 4
+        if self._halves is None:
+            if self._sd is None:
+                raise RuntimeError("load_state_dict first")
+            self._halves = []
+            for _ in range(2):
+                e = SynthesisEngine(num_ctas=half, **self._ctor)
+                e.load_state_dict(self._sd)
+                self._halves.append(dict(eng=e, stream=torch.cuda.Stream(device=self.device)))
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        dev = self.device
+        out = torch.empty(B, T, device=dev, dtype=torch.float32)
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        hold = [c, g, out]
+        for k, b0 in enumerate(range(0, B, tile)):
+            ch = self._halves[k % 2]
+            Bc = min(tile, B - b0)
+            ch["stream"].wait_event(ready)
+            with torch.cuda.stream(ch["stream"]):
+                o, _ = ch["eng"].generate(B=Bc, T=T, c=None if c is None else c[b0:b0 + Bc],
+                                          g=None if g is None else g[b0:b0 + Bc], seed=(seed + k) & 0x3FFFFFFFFFFFFFFF,
+                                          sync=False)
+                out[b0:b0 + Bc].copy_(o, non_blocking=True)
+                hold.append(o)
+        for ch in self._halves:
+            done = torch.cuda.Event()
+            done.record(ch["stream"])
+            cur.wait_event(done)
+        self._keep_conc = hold
+        if sync:
+            self.sync_concurrent()
+        return out
+
+    def sync_concurrent(self):
+        for ch in (self._halves or []):
+            ch["eng"].sync()
+        self._keep_conc = None
 
     def sync(self):
         N.check(N.lib().wn_sync(self._h))
