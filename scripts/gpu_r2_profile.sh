@@ -9,7 +9,7 @@ echo "== ncu launch list (shares, not absolutes)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-config4 --T 4000 > gpurun_out/r2_bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full set on the synthesis kernel (T=2000)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:wn7_kernel -c 1 -o gpurun_out/r2_prof \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:wn_persistent -c 1 -o gpurun_out/r2_prof \
     python scripts/ncu_target.py 2000 1 > gpurun_out/r2_ncu_full.log 2>&1; echo "ncu full rc=$?"
 if [ -f gpurun_out/r2_prof.ncu-rep ]; then
   ncu -i gpurun_out/r2_prof.ncu-rep --page raw --csv > gpurun_out/r2_prof_raw.csv 2>/dev/null

@@ -48,7 +48,7 @@ def main():
     out = {
         "kernel": col.get("Kernel Name", ("?",))[0],
         "workload": "BASELINE config 2, B=%d" % B, "T": T, "utts_per_gpu": B,
-        "capture": "ncu --set full --clock-control none --import-source on -k regex:wn7_kernel -c 1 python scripts/ncu_target.py %d %d" % (T, B),
+        "capture": "ncu --set full --clock-control none --import-source on -k regex:wn_persistent -c 1 python scripts/ncu_target.py %d %d" % (T, B),
         "duration_ms": dur_ms,
         "dram_bytes_per_launch": (rd or 0) + (wr or 0),
         "dram_bytes_per_sample": ((rd or 0) + (wr or 0)) / T,

@@ -34,7 +34,7 @@ def model_for(scales, cin_pad, net="ConvInUpsampleNetwork", C=80):
                 p.mul_(1.0 + 0.3 * torch.rand_like(p))
             if n_.endswith("weight_v"):
                 p.add_(0.05 * torch.randn_like(p))
-    return m.cuda().eval()
+    return m.eval()          # on the CPU: the caller takes the fp32 reference there before moving it
 
 
 @pytest.mark.parametrize("scales,cin_pad,net,frames", [([4, 4, 4, 4], 2, "ConvInUpsampleNetwork", 17),
@@ -45,11 +45,11 @@ def model_for(scales, cin_pad, net="ConvInUpsampleNetwork", C=80):
 def test_native_upsampler_matches_module(scales, cin_pad, net, frames):
     m = model_for(scales, cin_pad, net)
     B = 3
-    import copy
-    c = torch.randn(B, 80, frames + 2 * cin_pad).cuda()
+    c = torch.randn(B, 80, frames + 2 * cin_pad)
     with torch.no_grad():
         # fp32 reference on the CPU: cuDNN would run the conv_in / smoothing convolutions in TF32 by default
-        ref = copy.deepcopy(m.upsample_net).cpu()(c.cpu()).cuda()    # (B,C,T) module with the reference's structure
+        ref = m.upsample_net(c).cuda()                              # (B,C,T) module with the reference's structure
+    m, c = m.cuda(), c.cuda()
     T = ref.size(-1)
     eng = m._get_engine()
     assert m._native_upsample and eng.upsampled_length(c.size(-1)) == T

@@ -165,6 +165,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    alt = os.environ.get("WN_LIB_PATH")      # A/B experiments: load another build of the same ABI as it is
+    if alt:
+        return _bind(C.CDLL(alt))
     if needs_build():
         try:
             build()
@@ -173,7 +176,11 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("libwn.so not found at %s: run `python -c 'import __graft_entry__ as g; "
                            "g.build()'` (needs nvcc). There is no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    return _bind(C.CDLL(LIB_PATH))
+
+
+def _bind(L):
+    global _lib
     L.wn_abi_version.restype = C.c_int32
     L.wn_last_error.restype = C.c_char_p
     L.wn_create.argtypes = [C.POINTER(wn_config), C.POINTER(C.c_void_p)]

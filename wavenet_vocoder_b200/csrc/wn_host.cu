@@ -466,7 +466,7 @@ struct WnHandle {
     cudaStream_t last_stream = nullptr;
     bool pending = false;
     int64_t launches = 0;
-    bool attr_set[16] = {};
+    bool attr_set[20] = {};
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 carve-out
     int l2_mode = 0;                                  // WN_L2_PERSIST: 1 = packed weights, 2 = exchange buffer
     size_t wpack_bytes = 0;
@@ -557,6 +557,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.timeout_cycles = (long long)env_int("WN_TIMEOUT_MS", 2000) * 1500000LL;
     pp.warp_reverse = env_int("WN_WARP_REVERSE", 0);
     pp.gate_cycles = env_int("WN_GATE_CYCLES", 0);
+    pp.fast_gate = env_int("WN_FAST_GATE", 0);
     pp.prof = nullptr;
     if (env_int("WN_PROF", 0)) {
         const size_t pb = (size_t)pl.P * 16 * sizeof(long long);
@@ -571,6 +572,19 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     auto efor = [](int K) { return K <= 128 ? 1 : (K <= 256 ? 2 : (K <= 512 ? 4 : 8)); };
     const int er = efor(pl.R), eg = efor(pl.G2);
     const int var = (er == 1 && eg == 1) ? 0 : ((er <= 2 && eg <= 2) ? 1 : ((er <= 4 && eg <= 2) ? 2 : 3));
+    {
+        // lean stage path of the kernel (wn_kernel.cuh crit_loop): one utterance, vectors that fill the 128-thread
+        // groups exactly, one gate quad / residual quad / skip quad per block, kernel_size 3, chunk-aligned exchanges
+        static const int evar[4][2] = {{1, 1}, {2, 2}, {4, 2}, {8, 8}};
+        const int chunk = 1 << pl.xc_shift;
+        pl.lean = (BT == 1 && pl.ncopy == 1 && pl.kw == 3 && pl.RA == 4 && pl.NQ_A == 1 && pl.NQ_BO == 1 && pl.NQ_BS == 1 &&
+                   pl.NQ_D == 2 && pl.L >= 2 && evar[var][0] * 128 == pl.R && evar[var][1] * 128 == pl.G2 &&
+                   (evar[var][0] % 2) == 0 && (evar[var][1] % 2) == 0 && (pl.ex_yx % chunk) == 0 &&
+                   ((pl.G2 + pl.R) % chunk) == 0 && (pl.G2 % chunk) == 0 && (pl.xstride % 2) == 0 &&
+                   pl.S == pl.G2 && pl.NQ_HA == 1 && pl.NQ_HB == 1 && pl.O <= 128 && (pl.ex_sk % chunk) == 0 &&
+                   (pl.ex_h1 % chunk) == 0 &&
+                   env_int("WN_LEAN", 0) != 0) ? 1 : 0;
+    }
     const void* fn = nullptr;
 #define WN_PICK(BT_)                                                                          \
     fn = var == 0 ? (const void*)wn::wn_persistent_kernel<BT_, 1, 1>                          \
@@ -584,7 +598,11 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
         default: WN_PICK(8); break;
     }
 #undef WN_PICK
-    const int ai = bt_index(BT) * 4 + var;
+    if (pl.lean)      // the lean kernels: same plan, same packed weights, the lean stage path instead of the generic one
+        fn = var == 1 ? (const void*)wn::wn_persistent_kernel<1, 2, 2, true>
+           : var == 2 ? (const void*)wn::wn_persistent_kernel<1, 4, 2, true>
+                      : (const void*)wn::wn_persistent_kernel<1, 8, 8, true>;
+    const int ai = pl.lean ? 16 + var : bt_index(BT) * 4 + var;
     if (!h->attr_set[ai]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));
         h->attr_set[ai] = true;
