@@ -1,5 +1,6 @@
 # coding: utf-8
-"""Lean stage path == generic stage path, bit for bit (same arithmetic, same order):  python scripts/lean_check.py"""
+"""Lean stage path against the generic stage path on the same inputs (free running, same seed; the lean path adds the
+x-part of a gate pre-activation before the y-part, so the two differ by fp32 rounding):  python scripts/lean_check.py"""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,10 +32,11 @@ for name in ("cfg2", "cfg5"):
         outs[tag] = y.clone()
     for k in ("WN_LEAN", "WN_FAST_GATE"):
         os.environ.pop(k, None)
-    same = torch.equal(outs["generic"], outs["lean"])
+    d = float(((outs["generic"] - outs["lean"]) ** 2).mean().sqrt())
+    same = d <= 1e-4
     rms = float(((outs["generic"] - outs["lean_fast_gate"]) ** 2).mean().sqrt())
     first = int((outs["generic"] != outs["lean_fast_gate"]).float().argmax()) if rms > 0 else -1
-    print(name, "lean == generic:", same, "| fast gate: RMS diff %.3g, first differing sample %d" % (rms, first),
+    print(name, "lean vs generic RMS %.3g:" % d, same, "| fast gate: RMS diff %.3g, first differing sample %d" % (rms, first),
           "| finite:", bool(torch.isfinite(outs["lean"]).all()))
     ok = ok and same
 print("LEAN_CHECK", "PASS" if ok else "FAIL")

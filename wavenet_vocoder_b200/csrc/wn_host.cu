@@ -206,7 +206,7 @@ static int32_t build_plan(const wn_config& c, int batch, int num_sms, long long 
         const int nq1 = std::max(pl.NQ_A + pl.NQ_BO, std::max(pl.NQ_BS, std::max(pl.NQ_HA, pl.NQ_HB)));
         pl.red1_floats = nq1 * 4 * BT * 4 + 4;                // partial sums of the 4 warps of a group
         pl.sm_red1 = take(2LL * pl.red1_floats * 4, 16);
-        pl.red2_floats = (pl.NQ_D + pl.NQ_BS) * 4 * BT * 4 + 4;
+        pl.red2_floats = (pl.NQ_D + pl.NQ_BS + pl.NQ_BO) * 4 * BT * 4 + 4;   // + the residual rows (lean path, def_loop)
         pl.sm_red2 = take(2LL * pl.red2_floats * 4, 16);      // two buffers each, alternating by stage
         pl.sm_sb = take(2LL * pl.L * pl.RA4 * BT * 4, 16);     // static part + per-step pre-sum table
         pl.sm_cond = take(pl.C > 0 ? 2LL * pl.L * pl.RA4 * BT * 4 : 16, 16);
@@ -577,7 +577,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
         // groups exactly, one gate quad / residual quad / skip quad per block, kernel_size 3, chunk-aligned exchanges
         static const int evar[4][2] = {{1, 1}, {2, 2}, {4, 2}, {8, 8}};
         const int chunk = 1 << pl.xc_shift;
-        pl.lean = (BT == 1 && pl.ncopy == 1 && pl.kw == 3 && pl.RA == 4 && pl.NQ_A == 1 && pl.NQ_BO == 1 && pl.NQ_BS == 1 &&
+        pl.lean = (BT == 1 && (var == 1 || var == 2) && pl.ncopy == 1 && pl.kw == 3 && pl.RA == 4 && pl.NQ_A == 1 && pl.NQ_BO == 1 && pl.NQ_BS == 1 &&
                    pl.NQ_D == 2 && pl.L >= 2 && evar[var][0] * 128 == pl.R && evar[var][1] * 128 == pl.G2 &&
                    (evar[var][0] % 2) == 0 && (evar[var][1] % 2) == 0 && (pl.ex_yx % chunk) == 0 &&
                    ((pl.G2 + pl.R) % chunk) == 0 && (pl.G2 % chunk) == 0 && (pl.xstride % 2) == 0 &&
@@ -600,8 +600,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
 #undef WN_PICK
     if (pl.lean)      // the lean kernels: same plan, same packed weights, the lean stage path instead of the generic one
         fn = var == 1 ? (const void*)wn::wn_persistent_kernel<1, 2, 2, true>
-           : var == 2 ? (const void*)wn::wn_persistent_kernel<1, 4, 2, true>
-                      : (const void*)wn::wn_persistent_kernel<1, 8, 8, true>;
+                      : (const void*)wn::wn_persistent_kernel<1, 4, 2, true>;
     const int ai = pl.lean ? 16 + var : bt_index(BT) * 4 + var;
     if (!h->attr_set[ai]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cap));

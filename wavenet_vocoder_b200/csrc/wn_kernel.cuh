@@ -1064,23 +1064,20 @@ struct Engine {
             l_puba = pp.xbuf + wn_pair_index((long long)(pl.ex_h1 + a0 + max(it_a, 0)));
             l_pubb = pp.xbuf + wn_pair_index((long long)(pl.ex_h2 + b0 + max(it_b, 0)));
         }
-        // one lean poll: the thread's pairs of y (and x) of one exchange, straight into registers
-        auto lean_poll = [&](const uint2* base, uint32_t tag, bool with_x) {
-            uint4 ry[LY], rx[LX];
-            uint32_t spins = 0;
+        // lean polls: the thread's pairs of the y part / the x part of one exchange, straight into registers.  A load
+        // whose two tags were good is not issued again (every attempt of every block lands on the same few L2 lines,
+        // and those reads are what the publishing stores queue behind)
+        auto lean_poll_y = [&](const uint2* base, uint32_t tag) {
+            uint4 ry[LY];
+            uint32_t need = (1u << LY) - 1u, spins = 0;
             while (true) {
-                uint32_t bad = 0;
 #pragma unroll
-                for (int j = 0; j < LY; ++j) ry[j] = ld_pair2(base + lk_y[j]);
-                if (with_x) {
+                for (int j = 0; j < LY; ++j)
+                    if (need & (1u << j)) ry[j] = ld_pair2(base + lk_y[j]);
 #pragma unroll
-                    for (int j = 0; j < LX; ++j) rx[j] = ld_pair2(base + lk_x[j]);
-#pragma unroll
-                    for (int j = 0; j < LX; ++j) bad |= (rx[j].y ^ tag) | (rx[j].w ^ tag);
-                }
-#pragma unroll
-                for (int j = 0; j < LY; ++j) bad |= (ry[j].y ^ tag) | (ry[j].w ^ tag);
-                if (bad == 0) break;
+                for (int j = 0; j < LY; ++j)
+                    if (((ry[j].y ^ tag) | (ry[j].w ^ tag)) == 0u) need &= ~(1u << j);
+                if (need == 0u) break;
                 if (((++spins) & 63u) == 0 && wn_poll_check(s_abort, pp.err, spins, pp.timeout_cycles, tag, p)) {
                     dead = true;
                     break;
@@ -1091,12 +1088,27 @@ struct Engine {
                 yr[2 * j][0] = __uint_as_float(ry[j].x);
                 yr[2 * j + 1][0] = __uint_as_float(ry[j].z);
             }
-            if (with_x) {
+        };
+        auto lean_poll_x = [&](const uint2* base, uint32_t tag) {
+            uint4 rx[LX];
+            uint32_t need = (1u << LX) - 1u, spins = 0;
+            while (true) {
 #pragma unroll
-                for (int j = 0; j < LX; ++j) {
-                    xr[2 * j][0] = __uint_as_float(rx[j].x);
-                    xr[2 * j + 1][0] = __uint_as_float(rx[j].z);
+                for (int j = 0; j < LX; ++j)
+                    if (need & (1u << j)) rx[j] = ld_pair2(base + lk_x[j]);
+#pragma unroll
+                for (int j = 0; j < LX; ++j)
+                    if (((rx[j].y ^ tag) | (rx[j].w ^ tag)) == 0u) need &= ~(1u << j);
+                if (need == 0u) break;
+                if (((++spins) & 63u) == 0 && wn_poll_check(s_abort, pp.err, spins, pp.timeout_cycles, tag | 0x40000000u, p)) {
+                    dead = true;
+                    break;
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < LX; ++j) {
+                xr[2 * j][0] = __uint_as_float(rx[j].x);
+                xr[2 * j + 1][0] = __uint_as_float(rx[j].z);
             }
         };
         // one row quad times the y-shaped / x-shaped register vector (wq already offset by the thread's 8*gt floats)
@@ -1179,46 +1191,36 @@ struct Engine {
                             const float pre_a = l_pre[s * pl.RA4], pre_b = l_pre[s * pl.RA4 + 1];
                             const uint32_t tag = tagbase + (uint32_t)(s - 1);
                             const uint2* base = l_in0 + (long long)(s - 1) * l_inc;
-                            if (pp.gate_cycles > 0) { while (clock64() - t_pub < pp.gate_cycles) {} }
-                            lean_poll(base, tag, s >= 2);          // x_0 is already in registers
-                            WN_TICK(0);
                             float* xst = xs + (s & 1) * R;
                             float* yst = ys + (s & 1) * G2;
+                            // x_{s-1} was published by the DEFERRED groups half a stage ago (def_loop): normally one attempt,
+                            // and its product is formed while y_{s-1} is still travelling (x_0 is already in registers)
+                            if (s >= 2) lean_poll_x(base, tag);
 #pragma unroll
                             for (int j = 0; j < LX; ++j)
                                 *reinterpret_cast<float2*>(xst + 2 * gt + 2 * WN_NTC * j) = make_float2(xr[2 * j][0], xr[2 * j + 1][0]);
+                            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+                            lean_quad_x(W + l_zx, a4);
+                            float4 wy[2 * LY];          // weights of the y part: in registers before the data arrives
+#pragma unroll
+                            for (int j = 0; j < 2 * LY; ++j)
+                                wy[j] = *reinterpret_cast<const float4*>(W + l_zy + (2 * WN_NTC * (j >> 1) + (j & 1)) * 4);
+                            if (pp.gate_cycles > 0) { while (clock64() - t_pub < pp.gate_cycles) {} }
+                            WN_TICK(4);
+                            lean_poll_y(base, tag);
+                            WN_TICK(0);
+#pragma unroll
+                            for (int j = 0; j < 2 * LY; ++j) {
+                                const float yv = yr[j][0];
+                                a4[0] = fmaf(wy[j].x, yv, a4[0]); a4[1] = fmaf(wy[j].y, yv, a4[1]);
+                                a4[2] = fmaf(wy[j].z, yv, a4[2]); a4[3] = fmaf(wy[j].w, yv, a4[3]);
+                            }
+                            reduce_scatter<4>(a4, lane);
+                            float* r1 = red1 + (s & 1) * pl.red1_floats;
+                            if ((lane & 7) == 0) r1[(lane >> 3) * WN_GW + gw] = a4[0];
 #pragma unroll
                             for (int j = 0; j < LY; ++j)
                                 *reinterpret_cast<float2*>(yst + 2 * gt + 2 * WN_NTC * j) = make_float2(yr[2 * j][0], yr[2 * j + 1][0]);
-                            // rows [a_0, g_0, a_1, g_1] of layer s (acc[0..3]) and the block's rows of x_s (acc[4..7])
-                            float acc[8];
-#pragma unroll
-                            for (int v = 0; v < 8; ++v) acc[v] = 0.f;
-                            {
-                                const float *wzy = W + l_zy, *wzx = W + l_zx, *wxo = W + l_xo;
-#pragma unroll
-                                for (int j = 0; j < 2 * LY; ++j) {
-                                    const int ko = (2 * WN_NTC * (j >> 1) + (j & 1)) * 4;
-                                    const float4 a = *reinterpret_cast<const float4*>(wzy + ko);
-                                    const float4 b = *reinterpret_cast<const float4*>(wxo + ko);
-                                    const float yv = yr[j][0];
-                                    acc[0] = fmaf(a.x, yv, acc[0]); acc[1] = fmaf(a.y, yv, acc[1]);
-                                    acc[2] = fmaf(a.z, yv, acc[2]); acc[3] = fmaf(a.w, yv, acc[3]);
-                                    acc[4] = fmaf(b.x, yv, acc[4]); acc[5] = fmaf(b.y, yv, acc[5]);
-                                    acc[6] = fmaf(b.z, yv, acc[6]); acc[7] = fmaf(b.w, yv, acc[7]);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 2 * LX; ++j) {
-                                    const int ko = (2 * WN_NTC * (j >> 1) + (j & 1)) * 4;
-                                    const float4 a = *reinterpret_cast<const float4*>(wzx + ko);
-                                    const float xv = xr[j][0];
-                                    acc[0] = fmaf(a.x, xv, acc[0]); acc[1] = fmaf(a.y, xv, acc[1]);
-                                    acc[2] = fmaf(a.z, xv, acc[2]); acc[3] = fmaf(a.w, xv, acc[3]);
-                                }
-                            }
-                            reduce_scatter<8>(acc, lane);
-                            float* r1 = red1 + (s & 1) * pl.red1_floats;
-                            if ((lane & 3) == 0) r1[l_redw] = acc[0];
                             if (bar_or_n<1, WN_NTC>(dead)) { step_dead = true; break; }
                             if (gt == 0) {
                                 fence_cta();
@@ -1227,16 +1229,9 @@ struct Engine {
                             ++nstash;
                             WN_TICK(1);
                             if (it_y >= 0) {
-                                const float4 pa = *reinterpret_cast<const float4*>(r1 + l_reda);
-                                const float4 pg = *reinterpret_cast<const float4*>(r1 + l_reda + WN_GW);
-                                const float a = ((pa.x + pa.y) + (pa.z + pa.w)) + pre_a;
-                                const float g = ((pg.x + pg.y) + (pg.z + pg.w)) + pre_b;
+                                const float a = quad_sum(r1 + l_reda) + pre_a;
+                                const float g = quad_sum(r1 + l_reda + WN_GW) + pre_b;
                                 st_pair(l_puby + (long long)s * l_inc, pp.fast_gate ? gate_fast(a, g) : gate(a, g), tag + 1u);
-                            }
-                            if (it_x >= 0) {
-                                const float4 po = *reinterpret_cast<const float4*>(r1 + l_redx);
-                                const float o = ((po.x + po.y) + (po.z + po.w)) + W[l_xb];
-                                st_pair(l_pubx + (long long)s * l_inc, (o + xst[l_xs]) * RSQRT2, tag + 1u);
                             }
                             release_blob(t, s);
                             if (pp.gate_cycles > 0) t_pub = clock64();
@@ -1317,7 +1312,8 @@ struct Engine {
                         // ---- lean stage L, head 1, head 2 (same arithmetic as the generic code below)
                         tail_done = true;
                         const float* H = acquire_lean(t, L);
-                        lean_poll(l_in0 + (long long)(L - 1) * l_inc, tagbase + (uint32_t)(L - 1), true);
+                        lean_poll_x(l_in0 + (long long)(L - 1) * l_inc, tagbase + (uint32_t)(L - 1));
+                        lean_poll_y(l_in0 + (long long)(L - 1) * l_inc, tagbase + (uint32_t)(L - 1));
                         WN_TICK(0);
                         float* xst = xs + (L & 1) * R;
 #pragma unroll
@@ -1349,7 +1345,7 @@ struct Engine {
                         }
                         WN_TICK(3);
                         if (na > 0) {
-                            lean_poll(l_sk0, tagbase + (uint32_t)L, false);
+                            lean_poll_y(l_sk0, tagbase + (uint32_t)L);
                             float a4[4] = {0.f, 0.f, 0.f, 0.f};
                             lean_quad_y(H + pl.tb_Ha + 8 * gt, a4);
                             reduce_scatter<4>(a4, lane);
@@ -1359,7 +1355,7 @@ struct Engine {
                         if (it_a >= 0)
                             st_pair(l_puba, fmaxf(quad_sum(r1a + it_a * WN_GW) + H[pl.tb_Hab + it_a], 0.f), tagbase + (uint32_t)L + 1u);
                         if (nb > 0) {
-                            lean_poll(l_h10, tagbase + (uint32_t)L + 1u, false);
+                            lean_poll_y(l_h10, tagbase + (uint32_t)L + 1u);
                             float a4[4] = {0.f, 0.f, 0.f, 0.f};
                             lean_quad_y(H + pl.tb_Hb + 8 * gt, a4);
                             reduce_scatter<4>(a4, lane);
@@ -1489,12 +1485,56 @@ struct Engine {
         constexpr bool LEAN_T = LEAN;
         constexpr bool lean = LEAN;
         const int d_tap = (gt < nring_items) ? gt / pl.RA : 0, d_rr = (gt < nring_items) ? gt % pl.RA : 0;
-        auto lean_stage = [&](int s, int layer, const float* Td, const float* Sk, const float* skb) -> bool {
+        // the residual stream is published from here (threads 64.. of the group), half a stage before the critical
+        // group of any block asks for it: its poll then spins on y alone (a third of the exchange)
+        int d_x0r, d_nx;
+        wn_part(R, P, p, d_x0r, d_nx);
+        const int d_fx = (gt >= 64 && gt < 64 + d_nx) ? gt - 64 : -1;
+        uint2* d_pubx = pp.xbuf;
+        long long d_inc = 0;
+        if (lean) {
+            d_pubx = pp.xbuf + wn_pair_index((long long)pl.ex_yx) + wn_pair_index((long long)(G2 + d_x0r + max(d_fx, 0)));
+            d_inc = wn_pair_index((long long)(G2 + R));
+        }
+        const float RSQRT2 = 0.70710678118654752440f;         // math.sqrt(0.5), modules.py:162
+        auto lean_stage = [&](int t, int s, int layer, const float* Td, const float* Sk, const float* skb) -> bool {
             count_lean(s_stash_cnt, nstash + 1, 32u, 0x04000000u);
             ++nstash;
             WN_TICK(0);
             const float* xst = xs + (s & 1) * R;
             const float* yst = ys + (s & 1) * G2;
+            float* red = red2 + (s & 1) * pl.red2_floats;
+            // ---- phase 1: the block's rows of x_s, published at once (the critical groups of all blocks need them
+            // for stage s+1, before anything else this group produces)
+            // rows of x_s = (conv1x1_out_{s-1} y_{s-1} + b + x_{s-1}) sqrt(.5)  (modules.py:160-162), not in the tail stage
+            float accx[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* Wb = Sk ? Sk - pl.lb_Sk : nullptr;     // the blob of stage s
+            if (Sk) {
+                const float* wx = Wb + pl.lb_Xo + 8 * gt;
+#pragma unroll
+                for (int j = 0; j < EG / 2; ++j) {
+                    const float2 yv2 = *reinterpret_cast<const float2*>(yst + 2 * gt + 2 * WN_NTC * j);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a = *reinterpret_cast<const float4*>(wx + (2 * WN_NTC * j + h) * 4);
+                        const float yv = h ? yv2.y : yv2.x;
+                        accx[0] = fmaf(a.x, yv, accx[0]); accx[1] = fmaf(a.y, yv, accx[1]);
+                        accx[2] = fmaf(a.z, yv, accx[2]); accx[3] = fmaf(a.w, yv, accx[3]);
+                    }
+                }
+            }
+            if (Sk) {
+                reduce_scatter<4>(accx, lane);
+                if ((lane & 7) == 0) red[(12 + (lane >> 3)) * WN_GW + gw] = accx[0];
+                if (bar_or_n<2, WN_NTC>(dead)) dead = true;
+                if (!dead && d_fx >= 0) {
+                    const float4 q = *reinterpret_cast<const float4*>(red + (12 + d_fx) * WN_GW);
+                    const float o = ((q.x + q.y) + (q.z + q.w)) + Wb[pl.lb_xb + d_fx];
+                    st_pair(d_pubx + (long long)s * d_inc, (o + xst[d_x0r + d_fx]) * RSQRT2,
+                            (uint32_t)t * ((uint32_t)L + 3u) + 1u + (uint32_t)s);
+                }
+            }
+            // ---- phase 2: queued older-tap products and skip rows
             float acc[8], accs[4];
 #pragma unroll
             for (int v = 0; v < 8; ++v) acc[v] = 0.f;
@@ -1534,12 +1574,12 @@ struct Engine {
             }
             reduce_scatter<8>(acc, lane);
             reduce_scatter<4>(accs, lane);
-            float* red = red2 + (s & 1) * pl.red2_floats;
             if ((lane & 3) == 0) red[(lane >> 2) * WN_GW + gw] = acc[0];
             if (Sk != nullptr && (lane & 7) == 0) red[(8 + (lane >> 3)) * WN_GW + gw] = accs[0];
             WN_TICK(1);
             const bool d = bar_or_n<2, WN_NTC>(dead);
             if (!d) {
+
                 if (gt < nring_items) {
                     const int e = (layer * (kw - 1) + d_tap) * 3;
                     const float4 q = *reinterpret_cast<const float4*>(red + gt * WN_GW);
@@ -1563,7 +1603,7 @@ struct Engine {
         // (uses y; nullptr in the tail stage, where the critical group evaluates them itself)
         auto stage = [&](int t, int s, int layer, const float* Td, const float* Sk, const float* skb) {
             if constexpr (LEAN_T) {
-                if (lean) return lean_stage(s, layer, Td, Sk, skb);
+                if (lean) return lean_stage(t, s, layer, Td, Sk, skb);
             }
             wait_count<true>(s_stash_cnt, nstash + 1, 0x04000000u);
             ++nstash;
