@@ -126,7 +126,9 @@ typedef struct wn_generate_args {
     float* out_dense;          /* one-hot input, no QUANTIZE: (B,O,T) probabilities / logits  */
     float* params_out;         /* optional (B,O,T): head output per step (sampler input)      */
     void* stream;              /* cudaStream_t, NULL = default stream                         */
-    int32_t reserved[8];
+    int32_t philox_row0;       /* WN_NOISE_PHILOX: utterance b of this call draws the noise of row philox_row0 + b
+                                * (a batch split over several handles / calls then draws what one call would)  */
+    int32_t reserved[7];
 } wn_generate_args;
 
 /* What the planner decided (for tests, DESIGN.md numbers and the roofline arithmetic). */

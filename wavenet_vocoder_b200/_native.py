@@ -57,7 +57,8 @@ class wn_generate_args(C.Structure):
         ("noise_e", C.c_void_p),
         ("out_scalar", C.c_void_p), ("out_index", C.c_void_p), ("out_dense", C.c_void_p),
         ("params_out", C.c_void_p), ("stream", C.c_void_p),
-        ("reserved", C.c_int32 * 8),
+        ("philox_row0", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

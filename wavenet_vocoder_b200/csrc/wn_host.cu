@@ -547,7 +547,7 @@ static int32_t launch_chunk(WnHandle* h, const wn_generate_args* a, int b0, int 
     pp.params_out = a->params_out ? a->params_out + (size_t)b0 * O * T : nullptr;
     pp.B = Bc;
     pp.Btot = a->B;
-    pp.b0 = b0;
+    pp.b0 = b0 + a->philox_row0;          // only the Philox counters use it (wn_kernel.cuh fetch_noise)
     pp.T = T;
     pp.T_test = Tt;
     pp.initial_index = a->initial_index < 0 ? 127 : a->initial_index;   // wavenet.py:286
@@ -803,7 +803,7 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
     pp.params_out = a->params_out ? a->params_out + (size_t)b0 * O * T : nullptr;
     pp.B = Bc;
     pp.Btot = a->B;
-    pp.b0 = b0;
+    pp.b0 = b0 + a->philox_row0;
     pp.T = T;
     pp.T_test = Tt;
     pp.initial_index = a->initial_index < 0 ? 127 : a->initial_index;   // wavenet.py:286
