@@ -55,23 +55,27 @@ __global__ void frames_to_fc_kernel(const float* __restrict__ c, float* __restri
 //   level j:  a_j[u] = sum_{k=0}^{2s} w_j[k] * st[u + k - s],   st[v] = a_{j-1}[min(floor(v * rscale), n_{j-1}-1)] for
 //   0 <= v < n_j, 0 outside (Conv2d padding (0, s), upsample.py:41-43; Stretch2d upsample.py:19-21)
 template <int TS>
-__global__ void upsample_kernel(const float* __restrict__ h /* (B,F0,C) */, const float* __restrict__ filters, UpsampleDesc d,
+__global__ void upsample_kernel(const float* __restrict__ h /* (B,F0,C) */, const float* __restrict__ filters,
+                                const __grid_constant__ UpsampleDesc d,
                                 int C, int F0, int T_out, float* __restrict__ out /* (B,T_out,C) */) {
     extern __shared__ float sm[];
     const int b = blockIdx.y, t0 = blockIdx.x * TS;
     const int J = d.n_scales;
-    // length of every level and the index range this tile needs from it
-    int n[WNAUX_MAX_SCALES + 1], lo[WNAUX_MAX_SCALES + 1], hi[WNAUX_MAX_SCALES + 1];
-    n[0] = F0;
-    for (int j = 1; j <= J; ++j) n[j] = n[j - 1] * d.scales[j - 1];
-    lo[J] = t0 + d.indent;
-    hi[J] = min(t0 + TS, T_out) - 1 + d.indent;
-    for (int j = J; j >= 1; --j) {
-        const int s = d.scales[j - 1];
-        const int vlo = max(lo[j] - s, 0), vhi = min(hi[j] + s, n[j] - 1);
-        lo[j - 1] = min((int)floorf((float)vlo * d.rscale[j - 1]), n[j - 1] - 1);
-        hi[j - 1] = min((int)floorf((float)vhi * d.rscale[j - 1]), n[j - 1] - 1);
+    // length of every level and the index range this tile needs from it (block-uniform: one thread fills the table)
+    __shared__ int n[WNAUX_MAX_SCALES + 1], lo[WNAUX_MAX_SCALES + 1], hi[WNAUX_MAX_SCALES + 1];
+    if (threadIdx.x == 0) {
+        n[0] = F0;
+        for (int j = 1; j <= J; ++j) n[j] = n[j - 1] * d.scales[j - 1];
+        lo[J] = t0 + d.indent;
+        hi[J] = min(t0 + TS, T_out) - 1 + d.indent;
+        for (int j = J; j >= 1; --j) {
+            const int s = d.scales[j - 1];
+            const int vlo = max(lo[j] - s, 0), vhi = min(hi[j] + s, n[j] - 1);
+            lo[j - 1] = min((int)floorf((float)vlo * d.rscale[j - 1]), n[j - 1] - 1);
+            hi[j - 1] = min((int)floorf((float)vhi * d.rscale[j - 1]), n[j - 1] - 1);
+        }
     }
+    __syncthreads();
     // level 0 window from global memory
     float* cur = sm;
     float* nxt = sm + (size_t)(TS / 2 + 8) * C;      // every scale >= 2: a lower level's window is <= TS/2 + 3 entries

@@ -185,6 +185,11 @@ __device__ __forceinline__ bool bar_or_n(bool pred) {
     return r != 0;
 }
 
+// The barrier at which the two compute groups of a block meet (id 3, all WN_NT compute threads).  One out-of-line
+// instance: the groups arrive from two different loops, and tools that check barrier divergence (compute-sanitizer
+// synccheck) expect every participant of a barrier at the same instruction.
+__device__ __noinline__ bool bar_groups(bool pred) { return bar_or_n<3, WN_NT>(pred); }
+
 // NA independent value sets reduced in lock step (the shuffles of different sets overlap)
 template <int NA, int NV>
 __device__ __forceinline__ void reduce_scatter_multi(float (&v)[NA][NV], int lane) {
@@ -1018,7 +1023,7 @@ struct Engine {
         int nstash = 0;      // stashes published so far == deferred stages started
         int ndone = 0;       // deferred stages this group has waited for
         long long t_pub = clock64();
-        if (bar_or_n<3, WN_NT>(false)) return;      // the deferred group has built the pre-sums of step 0
+        if (bar_groups(false)) return;      // the deferred group has built the pre-sums of step 0
 
         // ---- lean stage path (pl.lean, set by wn_host.cu: one utterance, exact vector lengths, one gate quad and one
         // residual quad per block).  A stage is a chain of dependent instructions executed by one warp per SM
@@ -1430,11 +1435,11 @@ struct Engine {
                 WN_TICK(5);
             } while (false);
             // ---- both groups meet: sampler (one warp per utterance), then the next step
-            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            if (bar_groups(dead || step_dead)) return;
             // the deferred group finished its stage L before this barrier
             if (L >= 1) ++ndone;
             step_tail(t);
-            if (bar_or_n<3, WN_NT>(false)) return;
+            if (bar_groups(false)) return;
             WN_TICK(6);
         }
         if (prof) {
@@ -1452,10 +1457,11 @@ struct Engine {
                 if (b < pp.B) pp.params_out[((size_t)b * O + o) * T + t] = hs[i];
             }
             // the softmax sampler overwrites hs in place: finish the copy first (block-uniform)
-            if (pl.head_kind == 2) bar_or_n<3, WN_NT>(false);
+            if (pl.head_kind == 2) bar_groups(false);
         }
         if (warp < BT) {
             sample_utt(t, warp);
+            __syncwarp();                 // every lane has read step t's draws before they are overwritten
             if (t + 1 < T) fetch_noise(t + 1, warp);
         }
         // advance the ring positions to (t+1) mod delay
@@ -1653,7 +1659,7 @@ struct Engine {
         };
 
         build_pre(0);
-        if (bar_or_n<3, WN_NT>(dead)) return;
+        if (bar_groups(dead)) return;
         for (int t = 0; t < T; ++t) {
             if (prof) tc = clock64();
             bool step_dead = false;
@@ -1673,9 +1679,9 @@ struct Engine {
                 if (bar_or_n<2, WN_NTC>(dead)) step_dead = true;
                 else build_pre(t + 1);
             }
-            if (bar_or_n<3, WN_NT>(dead || step_dead)) return;
+            if (bar_groups(dead || step_dead)) return;
             step_tail(t);
-            if (bar_or_n<3, WN_NT>(false)) return;
+            if (bar_groups(false)) return;
             WN_TICK(3);
         }
         if (prof) {
