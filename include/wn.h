@@ -150,6 +150,10 @@ typedef struct wn_plan_info {
 } wn_plan_info;
 
 int32_t wn_abi_version(void);
+/* sizeof() of the structs of this header as the library was compiled, in the order wn_config, wn_weights,
+ * wn_generate_args, wn_plan_info, wn_upsampler; n = capacity of `out`, the return value the number written.  Lets a binding
+ * that transcribes the structs (ctypes, cgo, JNI) check its layout before the first real call. */
+int32_t wn_struct_sizes(int32_t* out, int32_t n);
 const char* wn_last_error(void);
 
 /* Create an engine for one model shape on one GPU.  Fails (WN_ERR_CUDA) without a device. */

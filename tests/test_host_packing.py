@@ -45,6 +45,11 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.wn_abi_version() == N.WN_ABI_VERSION
+    # the transcribed ctypes structs have the layout the library was compiled with
+    sizes = (C.c_int32 * 5)()
+    assert lib.wn_struct_sizes(sizes, 5) == 5
+    assert list(sizes) == [C.sizeof(t) for t in (N.wn_config, N.wn_weights, N.wn_generate_args, N.wn_plan_info,
+                                                   N.wn_upsampler)]
 
 
 def test_create_fails_loudly_without_gpu():

@@ -128,7 +128,7 @@ def plan_passes(cfg, batch=1, num_sms=148, smem=232448):
 
 
 # every symbol include/wn.h declares (tests check the .so exports all of them)
-EXPORTS = ["wn_abi_version", "wn_last_error", "wn_create", "wn_destroy", "wn_load_weights",
+EXPORTS = ["wn_abi_version", "wn_struct_sizes", "wn_last_error", "wn_create", "wn_destroy", "wn_load_weights",
            "wn_generate", "wn_sync", "wn_generate_host", "wn_get_plan", "wn_plan_only",
            "wn_pack_cta", "wn_plan_passes", "wn_load_upsampler", "wn_upsample", "wn_decode", "wn_sample_mol", "wn_sample_gauss"]
 
@@ -204,11 +204,20 @@ def _bind(L):
                                 C.c_void_p, C.c_void_p]
     L.wn_sample_gauss.argtypes = L.wn_sample_mol.argtypes
     for n in EXPORTS:
+        if n == "wn_struct_sizes" and not hasattr(L, n):
+            continue                       # an older build of the same ABI (A/B experiments through WN_LIB_PATH)
         fn = getattr(L, n)
         if n != "wn_last_error":
             fn.restype = C.c_int32
     if L.wn_abi_version() != WN_ABI_VERSION:
         raise RuntimeError("libwn.so ABI version mismatch")
+    sizes = (C.c_int32 * 5)()
+    if hasattr(L, "wn_struct_sizes"):
+        L.wn_struct_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]
+    if hasattr(L, "wn_struct_sizes") and L.wn_struct_sizes(sizes, 5) == 5:
+        mine = [C.sizeof(t) for t in (wn_config, wn_weights, wn_generate_args, wn_plan_info, wn_upsampler)]
+        if list(sizes) != mine:
+            raise RuntimeError("libwn.so struct layout mismatch: library %s, binding %s" % (list(sizes), mine))
     _lib = L
     return L
 

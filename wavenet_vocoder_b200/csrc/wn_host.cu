@@ -857,6 +857,13 @@ static int32_t launch_chunk7(WnHandle* h, const wn_generate_args* a, int b0, int
 extern "C" {
 
 int32_t wn_abi_version(void) { return WN_ABI_VERSION; }
+int32_t wn_struct_sizes(int32_t* out, int32_t n) {
+    const int32_t v[5] = {(int32_t)sizeof(wn_config), (int32_t)sizeof(wn_weights), (int32_t)sizeof(wn_generate_args),
+                          (int32_t)sizeof(wn_plan_info), (int32_t)sizeof(wn_upsampler)};
+    int32_t k = 0;
+    for (; k < 5 && k < n; ++k) out[k] = v[k];
+    return k;
+}
 const char* wn_last_error(void) { return g_err.c_str(); }
 
 int32_t wn_plan_only(const wn_config* cfg, int32_t batch, int32_t num_sms, int64_t smem_per_cta, wn_plan_info* out) {

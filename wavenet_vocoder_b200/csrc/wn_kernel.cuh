@@ -185,10 +185,15 @@ __device__ __forceinline__ bool bar_or_n(bool pred) {
     return r != 0;
 }
 
-// The barrier at which the two compute groups of a block meet (id 3, all WN_NT compute threads).  One out-of-line
-// instance: the groups arrive from two different loops, and tools that check barrier divergence (compute-sanitizer
-// synccheck) expect every participant of a barrier at the same instruction.
+// The barrier at which the two compute groups of a block meet (id 3, all WN_NT compute threads).  The groups arrive
+// from two different loops, which PTX allows (a barrier is its id, not its instruction) but compute-sanitizer's
+// synccheck reports as divergence: -DWN_SINGLE_BARRIER_SITE compiles ONE out-of-line instance for that tool
+// (profiles/r2_sanitizer_summary.txt).  The shipped build inlines it: the call costs 2 % of a sample (46.5 vs 45.4 us).
+#ifdef WN_SINGLE_BARRIER_SITE
 __device__ __noinline__ bool bar_groups(bool pred) { return bar_or_n<3, WN_NT>(pred); }
+#else
+__device__ __forceinline__ bool bar_groups(bool pred) { return bar_or_n<3, WN_NT>(pred); }
+#endif
 
 // NA independent value sets reduced in lock step (the shuffles of different sets overlap)
 template <int NA, int NV>
@@ -1461,7 +1466,9 @@ struct Engine {
         }
         if (warp < BT) {
             sample_utt(t, warp);
+#ifndef WN_NO_SAMPLER_SYNCWARP
             __syncwarp();                 // every lane has read step t's draws before they are overwritten
+#endif
             if (t + 1 < T) fetch_noise(t + 1, warp);
         }
         // advance the ring positions to (t+1) mod delay
