@@ -128,8 +128,9 @@ def time_cpu(model, n_samples, warm, threads, budget_s=25.0):
                 orc.incremental_forward(cfg, w, c=c, T=T, progress=progress)
         return time.perf_counter() - marks["t0"]
 
-    probe = run(10 + 30, 10) / 30.0                      # seconds per sample
-    n = int(max(50, min(n_samples, budget_s / max(probe, 1e-6))))
+    probe = run(3 + 5, 3) / 5.0                          # seconds per sample (an oversubscribed all-core run can need 2 s)
+    n = int(max(8, min(n_samples, budget_s / max(probe, 1e-6))))
+    warm = int(min(warm, max(3, 0.25 * budget_s / max(probe, 1e-6))))
     dt = run(warm + n, warm)
     return n / dt, dt, n, kind
 
