@@ -976,10 +976,13 @@ int32_t wn_create(const wn_config* cfg, void** handle) {
         delete h;
         return rc;
     }
-    h->l2_mode = env_int("WN_L2_PERSIST", 0);
+    h->l2_mode = env_int("WN_L2_PERSIST", 2);
     if (h->l2_mode > 0 && prop.persistingL2CacheMaxSize > 0) {
-        // Optional: WN_L2_PERSIST=1 pins as much of the packed weight image as allowed in the persisting part of the
-        // 126 MB L2 (measured 44.7 us/sample with the window vs 44.1 without); =2 pins the exchange buffer instead.
+        // WN_L2_PERSIST=2 (default): the exchange buffer (a few MB, every line written and read once per generated
+        // sample) lives in a 16 MB persisting carve-out of the 126 MB L2, so the 112 MB/sample weight stream does not
+        // evict it between two steps: 44.9 vs 45.4 us/sample, twice in a row on the same box (profiles/
+        // r2_lean_stage_sweeps.txt, last block).  This sets cudaLimitPersistingL2CacheSize for the device (process-wide).
+        // =1 pins as much of the packed weight image as allowed instead (measured slower: 45.4 vs 45.0); =0: nothing.
         const size_t want = h->l2_mode == 2 ? std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 16u << 20)
                                              : (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
